@@ -1,0 +1,191 @@
+/*
+ * fatiando_b200.h -- C ABI of the B200-native right-rectangular-prism
+ * potential-field forward model (libfatiando_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of fatiando/fatiando: the native
+ * module `fatiando.gravmag._prism` (reference: fatiando/gravmag/_prism.pyx,
+ * imported by fatiando/gravmag/prism.py:92-95) and the per-cell sensitivity
+ * build that callers layer on top of it (harvester.py:720-724,958-962,
+ * imaging.py:116-117, eqlayer.py:100-111).  Plain C types only: pointers,
+ * sizes, doubles.  Every entry point returns FB200_OK (0) or a negative
+ * FB200_E* code and never aborts; fb200_last_error() gives the message of the
+ * calling thread's last failure.
+ *
+ * Conventions (identical to the reference): x north, y east, z down, SI in;
+ * all arrays are IEEE binary64; a prism is the six bounds x1,x2,y1,y2,z1,z2.
+ * There is no CPU fallback anywhere behind this header: without a usable
+ * CUDA device every compute entry point fails with FB200_ECUDA.
+ */
+#ifndef FATIANDO_B200_H
+#define FATIANDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------ */
+#define FB200_OK        0
+#define FB200_EINVAL   -1   /* bad argument (null pointer, negative size, ...) */
+#define FB200_ECUDA    -2   /* CUDA runtime/driver error, no device, OOM      */
+#define FB200_EPROP    -3   /* field needs a property the model does not hold */
+#define FB200_EUNSUP   -4   /* unsupported combination of flags               */
+
+/* ---- field ids; bit (1u << id) in a field mask -------------------------
+ * Order = the 14 accumulators of _prism.pyx: potential :454, gx :196,
+ * gy :223, gz :250, gxx :277, gxy :304, gxz :336, gyy :368, gyz :395,
+ * gzz :427, tf :72, bx :106, by :136, bz :166.                              */
+enum fb200_field {
+    FB200_POTENTIAL = 0, FB200_GX = 1, FB200_GY = 2, FB200_GZ = 3,
+    FB200_GXX = 4, FB200_GXY = 5, FB200_GXZ = 6, FB200_GYY = 7,
+    FB200_GYZ = 8, FB200_GZZ = 9, FB200_TF = 10, FB200_BX = 11,
+    FB200_BY = 12, FB200_BZ = 13, FB200_NFIELDS = 14
+};
+#define FB200_GRAVITY_MASK  0x03FFu
+#define FB200_MAGNETIC_MASK 0x3C00u
+
+/* ---- flags ------------------------------------------------------------- */
+/* xp/yp/zp/out (and init) are device pointers on the model's device        */
+#define FB200_DEVICE_POINTERS  (1u << 0)
+/* evaluate in the reference's exact operation order (corner by corner,
+ * running accumulator, libdevice log/atan2) instead of the fused fast path  */
+#define FB200_REFERENCE_ORDER  (1u << 1)
+/* jacobian only: write the transpose, out[cell * ld + point]
+ * (the layout imaging.py:116-117 builds)                                    */
+#define FB200_TRANSPOSED       (1u << 2)
+
+typedef struct fb200_model fb200_model;
+
+/* ---- housekeeping ------------------------------------------------------ */
+int         fb200_abi_version(void);
+const char *fb200_last_error(void);
+/* number of CUDA devices visible to this process (0 and FB200_ECUDA if none) */
+int         fb200_device_count(int *count);
+/* name / SM count / memory of a device, for logs                            */
+int         fb200_device_info(int device, char *name, int name_len,
+                              int *sm_count, int64_t *total_mem_bytes);
+
+/* ---- the mesh flattener's upload: SoA prism data, copied to HBM once ----
+ * Replaces the per-prism attribute reads of prism.py:138-140 (bounds) and
+ * :134-137 / :650-655 (properties).  x1..z2 are host arrays of m doubles.
+ * density may be NULL (model usable for magnetic fields only, or with a
+ * density override); mx,my,mz are all NULL or all non-NULL.  Prisms are kept
+ * in the order given; that order is the summation order.                     */
+int fb200_model_create(int device, int64_t m,
+                       const double *x1, const double *x2,
+                       const double *y1, const double *y2,
+                       const double *z1, const double *z2,
+                       const double *density,
+                       const double *mx, const double *my, const double *mz,
+                       fb200_model **out);
+int     fb200_model_destroy(fb200_model *model);
+int64_t fb200_model_size(const fb200_model *model);
+int     fb200_model_device(const fb200_model *model);
+
+/* ---- forward fields: the loop of prism.py:131-141 over a whole model ----
+ * For every point l and every field f in field_mask (ascending id order):
+ *   out[c * ld_out + l] = scale[c] * sum over prisms of field f
+ * c = 0,1,... numbering the requested fields.  One pass evaluates all
+ * requested components and shares the per-corner r / log / atan2 work.
+ *   dens_override : NULL, or pointer to one double used instead of every
+ *                   prism's density (prism.py:134-137, `dens=`).
+ *   pmag_override : NULL, or 3 doubles used instead of every prism's
+ *                   magnetization (prism.py:641-645, `pmag=`).
+ *   fvec          : 3 direction cosines of the inducing field; required when
+ *                   FB200_TF is requested (prism.py:640), ignored otherwise.
+ *   scale         : one factor per requested field (e.g. G*SI2MGAL,
+ *                   prism.py:286); NULL means 1.0 for all.
+ * Host pointers by default; with FB200_DEVICE_POINTERS all of xp,yp,zp,out
+ * are device pointers and nothing is copied.                                 */
+int fb200_forward(fb200_model *model,
+                  const double *xp, const double *yp, const double *zp,
+                  int64_t n, uint32_t field_mask,
+                  const double *dens_override, const double *pmag_override,
+                  const double *fvec, const double *scale,
+                  double *out, int64_t ld_out, uint32_t flags);
+
+/* ---- sensitivity (Jacobian) matrix --------------------------------------
+ * out[l * ld + q] = scale * field(point l, prism q alone, unit property):
+ * column q is what prism.<field>(x, y, z, [cell_q], dens=1) returns
+ * (eqlayer.py:108-111 layout, harvester.py:720-724 / imaging.py:116-117
+ * call pattern).  unit_prop: 1 double (gravity) or 3 (magnetic; for
+ * FB200_TF the unit magnetization vector, harvester.py:958-962).  fvec as in
+ * fb200_forward.  With FB200_TRANSPOSED, out[q * ld + l].
+ * With host `out` the matrix is streamed back in row blocks; with
+ * FB200_DEVICE_POINTERS it stays resident in HBM (row-sharded by the caller
+ * across GPUs by passing each GPU its slice of points).                      */
+int fb200_jacobian(fb200_model *model,
+                   const double *xp, const double *yp, const double *zp,
+                   int64_t n, int field, const double *unit_prop,
+                   const double *fvec, double scale,
+                   double *out, int64_t ld, uint32_t flags);
+
+/* ---- the reference's own FFI shape: one prism accumulated into res ------
+ * `_prism.<field>(xp, yp, zp, x1, x2, y1, y2, z1, z2, <props>, res)` adds ONE
+ * prism's effect into caller-owned res[0..n) and never zeroes it
+ * (_prism.pyx:72-479).  Host pointers.  Evaluated in reference order with
+ * res[l] as the starting value of the running sum.                           */
+int fb200_prism_potential(const double *xp, const double *yp, const double *zp, int64_t n,
+                          double x1, double x2, double y1, double y2, double z1, double z2,
+                          double density, double *res);          /* _prism.pyx:454 */
+int fb200_prism_gx(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double density, double *res);                 /* _prism.pyx:196 */
+int fb200_prism_gy(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double density, double *res);                 /* _prism.pyx:223 */
+int fb200_prism_gz(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double density, double *res);                 /* _prism.pyx:250 */
+int fb200_prism_gxx(const double *xp, const double *yp, const double *zp, int64_t n,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double density, double *res);                /* _prism.pyx:277 */
+int fb200_prism_gxy(const double *xp, const double *yp, const double *zp, int64_t n,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double density, double *res);                /* _prism.pyx:304 */
+int fb200_prism_gxz(const double *xp, const double *yp, const double *zp, int64_t n,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double density, double *res);                /* _prism.pyx:336 */
+int fb200_prism_gyy(const double *xp, const double *yp, const double *zp, int64_t n,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double density, double *res);                /* _prism.pyx:368 */
+int fb200_prism_gyz(const double *xp, const double *yp, const double *zp, int64_t n,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double density, double *res);                /* _prism.pyx:395 */
+int fb200_prism_gzz(const double *xp, const double *yp, const double *zp, int64_t n,
+                    double x1, double x2, double y1, double y2, double z1, double z2,
+                    double density, double *res);                /* _prism.pyx:427 */
+int fb200_prism_tf(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double mx, double my, double mz, double fx, double fy, double fz,
+                   double *res);                                 /* _prism.pyx:72  */
+int fb200_prism_bx(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double mx, double my, double mz, double *res); /* _prism.pyx:106 */
+int fb200_prism_by(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double mx, double my, double mz, double *res); /* _prism.pyx:136 */
+int fb200_prism_bz(const double *xp, const double *yp, const double *zp, int64_t n,
+                   double x1, double x2, double y1, double y2, double z1, double z2,
+                   double mx, double my, double mz, double *res); /* _prism.pyx:166 */
+
+/* ---- measurement helpers (used by bench.py; not part of the data path) --
+ * Device time in milliseconds of the kernels launched by the most recent
+ * fb200_forward / fb200_jacobian call on this model (CUDA events on the
+ * model's stream), and how many kernels that call launched.                  */
+int fb200_last_kernel_ms(const fb200_model *model, double *ms, int *launches);
+/* Register-resident DFMA-chain microbenchmark: the FP64 roofline denominator
+ * that MEASURED_PEAKS.json does not carry.  Runs for about `seconds`, returns
+ * the best (burst) and the whole-run (sustained) rate in TFLOP/s (DFMA = 2). */
+int fb200_fp64_peak(int device, double seconds, double *burst_tflops,
+                    double *sustained_tflops);
+/* Device-wide L2 flush: overwrite a buffer larger than L2 (bench hygiene).   */
+int fb200_flush_l2(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FATIANDO_B200_H */

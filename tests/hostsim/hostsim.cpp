@@ -1,0 +1,60 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Compiles the device math headers of fatiando_b200/csrc (prism_exact.cuh,
+// prism_fast.cuh) for the HOST, so that the numerics of the fused fast path
+// (collapsed log/atan sums, custom log_ratio / atan) can be compared with the
+// oracle in a container that has no GPU.  Only tests/ builds and loads this;
+// fatiando_b200 never does -- the product has no CPU path.
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared (tests/hostsim/Makefile)
+#include <cstddef>
+#include <cstdint>
+#include "../../fatiando_b200/csrc/prism_masks.h"
+#include "../../fatiando_b200/csrc/prism_fast.cuh"
+
+using namespace fb200;
+
+template <uint32_t MASK, class Eval>
+static void run(const double *xp, const double *yp, const double *zp, size_t n, size_t m,
+                const double *const *b, const double *const *p, const double *f, double *out)
+{
+    constexpr int NC = popc(MASK);
+    const double fv[3] = {f[0], f[1], f[2]};
+    for (size_t l = 0; l < n; ++l) {
+        double acc[NC];
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+        for (size_t q = 0; q < m; ++q)
+            Eval::template pair<MASK>(acc, xp[l], yp[l], zp[l], b[0][q], b[1][q], b[2][q], b[3][q],
+                                      b[4][q], b[5][q], p[0][q], p[1] ? p[1][q] : 0.0,
+                                      p[2] ? p[2][q] : 0.0, fv);
+        for (int c = 0; c < NC; ++c) out[(size_t)c * n + l] = acc[c];
+    }
+}
+
+extern "C" int hostsim_forward(uint32_t mask, int exact, const double *xp, const double *yp,
+                               const double *zp, size_t n, size_t m, const double *const *bounds,
+                               const double *const *props, const double *fvec, double *out)
+{
+#define CASE(M)                                                                         \
+    if (mask == (M)) {                                                                  \
+        if (exact) run<(M), EvalExact>(xp, yp, zp, n, m, bounds, props, fvec, out);     \
+        else run<(M), EvalFast>(xp, yp, zp, n, m, bounds, props, fvec, out);            \
+        return 0;                                                                       \
+    }
+    FB200_GRAVITY_SETS(CASE)
+    FB200_MAGNETIC_SETS(CASE)
+#undef CASE
+    return -1;
+}
+
+extern "C" void hostsim_log_ratio(const double *num, const double *den, size_t n, double *out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = fm::log_ratio(num[i], den[i]);
+}
+extern "C" void hostsim_atan_rhp(const double *im, const double *re, size_t n, double *out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = fm::atan_rhp(im[i], re[i]);
+}
+extern "C" void hostsim_div(const double *a, const double *b, size_t n, double *out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = fm::div_fast(a[i], b[i]);
+}
