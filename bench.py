@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""
+Benchmark of the prism forward model on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5]
+    python bench.py --impl reference ...          # the reference's CPU path, same metric
+
+Metric (BASELINE.json): prism x point evaluations per second, fp64.  One "step" is
+one pass of the hot path over the whole workload.  Default workload = config C2
+(configs[1]): the six gravity-gradient components of a 50x50x20 PrismMesh with
+variable density on a 200x200 grid (2e9 pairs/step/GPU).  With N GPUs the
+observation grid is N times larger and observation-sharded (weak scaling, no
+data-path collective); value = all pairs of all ranks / max-over-ranks device time.
+
+  value    : inputs resident in HBM (device pointers through the C ABI), device time
+             from CUDA events on the library's own stream, summed over the K steps.
+  e2e      : the public Python API (prism.fields) with HOST numpy arrays: mesh
+             flattening, model upload, point H2D, kernels, result D2H, every step.
+  roofline : FP64 pipe.  achieved = pairs/s x F, F = SURVEY 8(d)'s fused-minimal FLOP
+             per pair of the REFERENCE formulation (what the answer costs with
+             libdevice-grade log/atan2 per corner); peak = DFMA-chain rate measured
+             in this run (MEASURED_PEAKS.json has no FP64 figure).  The kernel uses
+             an algebraically collapsed formulation with fewer instructions, so
+             achieved/peak can exceed 1; "executed_frac" is the real FP64-pipe
+             utilisation = executed FP64 instr/pair (ncu, profiles/) x pairs/s / issue rate.
+  cpu_baseline : the reference's own Cython kernel (oracle/_ref, "reference") or the C
+             port ("port") on this box's host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "prism_point_evals_per_s"
+UNIT = "pairs/s"
+
+# algorithmic work per prism x point pair of the reference
+# formulation fused into one pass (FLOP, DFMA = 2) and FP64-pipe slots.
+WORK = {
+    "c2": dict(flop=2802.0, slots=1922.0, what="6 tensor components"),
+    "c3": dict(flop=2820.0, slots=1940.0, what="tf+bx+by+bz"),
+    "c4": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
+    "c5": dict(flop=1478.0, slots=1022.0, what="gz"),
+    "c5t": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
+}
+# FP64-pipe instructions the fast kernels actually execute per pair (ncu
+# smsp__inst_executed_pipe_fp64 / pairs, see profiles/); None until measured.
+EXECUTED_FP64_PER_PAIR = {"c2": None, "c3": None, "c4": None, "c5": None, "c5t": None}
+
+
+# --------------------------------------------------------------------------
+# workloads (SURVEY.md 8(d) "Synthetic inputs"), all seeded
+# --------------------------------------------------------------------------
+def make_workload(name, world=1):
+    from fatiando_b200 import mesher, gridder, utils
+    rs = np.random.RandomState
+    if name == "c2":
+        mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (20, 50, 50))
+        mesh.addprop('density', rs(0).uniform(-1000, 1000, mesh.size))
+        xp, yp, zp = gridder.regular((0, 5000, 0, 5000), (200 * world, 200), z=-150)
+        return dict(model=mesh, prop='density', names=['gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz'],
+                    xp=xp, yp=yp, zp=zp, fvec=None, kind='forward',
+                    label="C2: gxx..gzz of PrismMesh 50x50x20 (5e4 prisms, variable density) on a "
+                          "%dx200 grid at z=-150" % (200 * world))
+    if name == "c3":
+        mesh = mesher.PrismMesh((0, 10000, 0, 10000, 0, 2000), (10, 100, 100))
+        inc, dec = 30, -15
+        r = rs(1)
+        mi = r.uniform(0.5, 2, mesh.size)
+        ri = r.uniform(0, 1, mesh.size)
+        ii = r.uniform(-90, 90, mesh.size)
+        di = r.uniform(-180, 180, mesh.size)
+        d2r = np.pi / 180.
+        rem = np.stack([ri * np.cos(d2r * ii) * np.cos(d2r * di),
+                        ri * np.cos(d2r * ii) * np.sin(d2r * di), ri * np.sin(d2r * ii)], axis=1)
+        mag = utils.ang2vec(mi, inc, dec) + rem
+        mesh.addprop('magnetization', mag)
+        xp, yp, zp = gridder.regular((0, 10000, 0, 10000), (500 * world, 500), z=-300)
+        return dict(model=mesh, prop='magnetization', names=['tf', 'bx', 'by', 'bz'],
+                    xp=xp, yp=yp, zp=zp, fvec=utils.dircos(inc, dec), kind='forward',
+                    label="C3: tf+bx+by+bz of PrismMesh 100x100x10 (1e5 prisms, induced+remanent) "
+                          "on a %dx500 grid at z=-300" % (500 * world))
+    if name == "c4":
+        mesh = mesher.PrismMesh((0, 10000, 0, 10000, 0, 4000), (16, 50, 50))
+        # one GPU holds a row block of J: 31250 x 40000 fp64 = 10 GB (1/8 of the 80 GB matrix)
+        xp, yp, zp = gridder.regular((0, 10000, 0, 10000), (500, 500), z=-100)
+        rows = 31250
+        idx = np.arange(rows * world)
+        return dict(model=mesh, prop=None, names=['gz'], xp=xp[idx], yp=yp[idx], zp=zp[idx],
+                    fvec=None, kind='jacobian',
+                    label="C4: gz sensitivity matrix, %d rows (of 250000) x 40000 PrismMesh cells, "
+                          "device-resident" % (rows * world))
+    if name in ("c5", "c5t"):
+        area, shape = (0, 1e6, 0, 1e6), (1000, 1000)
+        x, y = gridder.regular(area, shape)
+        r = rs(2)
+        h = np.zeros(x.size)
+        for _ in range(8):
+            h += r.uniform(500, 4000) * utils.gaussian2d(x, y, r.uniform(5e4, 2e5), r.uniform(5e4, 2e5),
+                                                        r.uniform(0, 1e6), r.uniform(0, 1e6),
+                                                        angle=r.uniform(0, 180))
+        h += r.uniform(0, 200, x.size)
+        relief = mesher.PrismRelief(0, gridder.spacing(area, shape), (x, y, -h))
+        relief.props['density'] = np.where(-h > 0, -2670.0, 2670.0)   # addprop's sign rule, vectorised
+        # 1/64 of the 1e6 points per GPU per step keeps a default run within minutes
+        xp, yp, zp = gridder.regular(area, (1000, 1000), z=-5000)
+        take = 15625 * world
+        idx = np.linspace(0, xp.size - 1, take).astype(np.int64)
+        names = ['gz'] if name == "c5" else ['gz', 'gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz']
+        return dict(model=relief, prop='density', names=names, xp=xp[idx].copy(), yp=yp[idx].copy(),
+                    zp=zp[idx].copy(), fvec=None, kind='forward',
+                    label="C5: %s of a 1000x1000 PrismRelief (1e6 prisms) at %d of the 1e6 points, "
+                          "z=-5000" % ('+'.join(names), take))
+    raise SystemExit("unknown workload %s" % name)
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU baseline: the reference's own kernel on this box's host cores
+# --------------------------------------------------------------------------
+def _cpu_chunk(args):
+    names, xp, yp, zp, bounds, props, fvec, kind = args
+    from oracle import prism_oracle as po
+    use_ref = po.ref_available()
+    out = 0.0
+    for f in names:
+        pr = props
+        if f == 'tf':
+            pr = np.hstack([props, np.tile(fvec, (props.shape[0], 1))])
+        if kind == 'jacobian':
+            # one reference call per cell (eqlayer.py:108-111): a column each
+            unit = np.ones((1, 1))
+            for q in range(bounds[0].size):
+                bq = [b[q:q + 1] for b in bounds]
+                col = po.ref_model(f, xp, yp, zp, bq, unit) if use_ref else po.model(f, xp, yp, zp, bq, unit)
+                out += float(col[0])
+        else:
+            r = po.ref_model(f, xp, yp, zp, bounds, pr) if use_ref else po.model(f, xp, yp, zp, bounds, pr)
+            out += float(r[0])
+    return out
+
+
+def cpu_baseline(w, flat, seconds=15.0, cores=None):
+    """pairs/s of the reference CPU path on a bounded sample of workload w."""
+    import multiprocessing as mp
+    from oracle import prism_oracle as po
+    cores = cores or os.cpu_count() or 1
+    m = flat.size
+    if w['prop'] == 'magnetization':
+        props = flat.magnetization
+    elif flat.density is not None:
+        props = flat.density[:, None]
+    else:
+        props = np.ones((m, 1))
+    bounds = flat.bounds
+    per_field_rate = 2.5e6       # pairs/s/core, order of magnitude
+    pts_per_core = max(1, int(per_field_rate * seconds / (m * len(w['names']))))
+    n_s = min(w['xp'].size, pts_per_core * cores)
+    idx = np.linspace(0, w['xp'].size - 1, n_s).astype(np.int64)
+    xs, ys, zs = w['xp'][idx].copy(), w['yp'][idx].copy(), w['zp'][idx].copy()
+    edges = np.linspace(0, n_s, min(cores, n_s) + 1).astype(int)
+    jobs = [(w['names'], xs[a:b], ys[a:b], zs[a:b], bounds, props, w['fvec'], w['kind'])
+            for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(jobs)) as pool:
+        warm = [(j[0], j[1][:1], j[2][:1], j[3][:1]) + j[4:] for j in jobs]
+        pool.map(_cpu_chunk, warm)                  # import + page-in, one point per worker
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, jobs)
+        dt = time.perf_counter() - t0
+    pairs = float(n_s) * m
+    return {"value": pairs / dt, "unit": UNIT, "cores": len(jobs),
+            "kind": "reference" if po.ref_available() else "port",
+            "sample": "%d of %d points x all %d prisms, %d field call(s) each (%s), %.1f s" % (
+                n_s, w['xp'].size, m, len(w['names']), '+'.join(w['names']), dt),
+            "seconds": dt}
+
+
+# --------------------------------------------------------------------------
+def dist_setup(gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def run_reference(args):
+    world, rank, _ = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    from fatiando_b200.flatten import flatten
+    w = make_workload(args.workload, 1)
+    flat = flatten(w['model'], w['prop'], override=w['prop'] is None, fvec=w['fvec'])
+    steps = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(w, flat, seconds=max(2.0, 60.0 / (args.warmup + args.steps)))
+        if i >= args.warmup:
+            steps.append(r)
+    value = float(np.mean([s['value'] for s in steps]))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean([s['seconds'] for s in steps])),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (seeded)", "config": {"workload": w['label']},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": steps[0]['cores'],
+                             "kind": steps[0]['kind'], "sample": steps[0]['sample']},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    from fatiando_b200 import _lib, prism
+    from fatiando_b200.flatten import flatten
+    import ctypes
+
+    world, rank, local = dist_setup(args.gpus)
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.require_device()
+    dev = local
+    lib = _lib.lib()
+
+    w = make_workload(args.workload, world)
+    from fatiando_b200.partition import local_slice
+    sl = local_slice(w['xp'].size, rank, world)
+    xp, yp, zp = (np.ascontiguousarray(a[sl]) for a in (w['xp'], w['yp'], w['zp']))
+    n = xp.size
+    flat = flatten(w['model'], w['prop'], override=w['prop'] is None, fvec=w['fvec'])
+    m = flat.size
+    names = w['names']
+    ncomp = len(names)
+    model = prism.Model(flat, w['prop'], device=dev)
+    tdev = torch.device("cuda", dev)
+    d_pts = [torch.from_numpy(a).to(tdev) for a in (xp, yp, zp)]
+    ids = sorted(_lib.FIELD_ID[nm] for nm in names)
+    mask = sum(1 << i for i in ids)
+    scale = np.array([prism.unit_scale(_lib.FIELDS[i]) for i in ids])
+    fvec = None if w['fvec'] is None else np.ascontiguousarray(w['fvec'], dtype=np.float64)
+    if w['kind'] == 'jacobian':
+        d_out = torch.empty((n, m), dtype=torch.float64, device=tdev)
+    else:
+        d_out = torch.empty((ncomp, n), dtype=torch.float64, device=tdev)
+    unit = np.array([1.0])
+    torch.cuda.synchronize()
+
+    def step_device():
+        if w['kind'] == 'jacobian':
+            rc = lib.fb200_jacobian(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
+                                    d_pts[2].data_ptr(), n, ids[0], _lib.dptr(unit), _lib.dptr(fvec),
+                                    float(scale[0]), d_out.data_ptr(), m, _lib.DEVICE_POINTERS)
+        else:
+            rc = lib.fb200_forward(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
+                                   d_pts[2].data_ptr(), n, mask, None, None, _lib.dptr(fvec),
+                                   _lib.dptr(scale), d_out.data_ptr(), n, _lib.DEVICE_POINTERS)
+        _lib.check(rc)
+        return model.last_kernel_ms()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    dev_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _lib.check(lib.fb200_flush_l2(dev))        # L2 hygiene, outside the step's events
+        ms, nl = step_device()
+        dev_ms += ms
+        launches += nl
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- e2e: public API, host buffers, everything inside the timed region ----
+    def step_e2e():
+        if w['kind'] == 'jacobian':
+            rows = min(n, 2048)      # host-resident J is PCIe-bound: bounded row block
+            j = prism.jacobian(xp[:rows], yp[:rows], zp[:rows], w['model'], names[0])
+            return rows, j.nbytes
+        if w['prop'] == 'magnetization':
+            res = prism._magnetic(names, xp, yp, zp, w['model'], None, w['fvec'], 'shape', device=dev)
+        else:
+            res = prism._gravity(names, xp, yp, zp, w['model'], None, 'shape', device=dev)
+        return n, sum(v.nbytes for v in res.values())
+    step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        rows_done, d2h = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t1) / e2e_steps
+    h2d = (6 + (3 if w['prop'] == 'magnetization' else (1 if w['prop'] else 0))) * m * 8 + 3 * rows_done * 8
+
+    # ---- reduce over ranks: max time, summed work ----
+    stats = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device=tdev)
+    work = torch.tensor([float(n) * m, float(rows_done) * m, float(launches)], dtype=torch.float64, device=tdev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_max, wall_max = stats.tolist()
+    pairs_step, pairs_e2e, launches_all = work.tolist()
+    ms_per_step = dev_ms_max / args.steps
+    value = pairs_step / (ms_per_step * 1e-3)
+
+    line = None
+    if rank == 0:
+        wk = WORK[args.workload]
+        burst, sustained = ctypes.c_double(0), ctypes.c_double(0)
+        _lib.check(lib.fb200_fp64_peak(dev, 1.0, ctypes.byref(burst), ctypes.byref(sustained)))
+        per_gpu = value / world
+        achieved = per_gpu * wk['flop'] / 1e12
+        peak = sustained.value if ms_per_step > 500 else burst.value
+        executed = EXECUTED_FP64_PER_PAIR.get(args.workload)
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak if peak else None, "traffic": None,
+                    "peak_source": "DFMA-chain microbenchmark in this run (fb200_fp64_peak: burst %.2f, "
+                                   "sustained %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 figure"
+                                   % (burst.value, sustained.value),
+                    "algorithmic_flop_per_pair": wk['flop'], "algorithmic_of": wk['what'],
+                    "executed_fp64_inst_per_pair": executed,
+                    "executed_frac": (per_gpu * executed / (148 * 32 * sm_hz / 2.0 * 1.0)
+                                      if executed else None)}
+        if w['kind'] == 'jacobian':
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            roofline["hbm_write"] = {"achieved_gbs": per_gpu * 8 / 1e9, "peak_gbs": hbm,
+                                     "frac": per_gpu * 8 / 1e9 / hbm,
+                                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            w1 = make_workload(args.workload, 1)
+            cpu = cpu_baseline(w1, flat, seconds=15.0)
+            cpu.pop("seconds", None)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (seeded numpy RandomState)",
+                "config": {"workload": w['label'], "pairs_per_step": pairs_step,
+                           "fields": names, "parallelism": "obs-shard x%d" % world,
+                           "l2": "flushed between steps (256 MiB memset); inputs (<4 MB) are "
+                                 "smem/L2-resident by design, kernel is FP64-bound"},
+                "wall_ms_per_step": 1e3 * wall_max / args.steps,
+                "e2e": {"value": pairs_e2e / e2e_max, "unit": UNIT,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "api": "fatiando_b200.prism (flatten + upload + H2D + kernels + D2H per step)"},
+                "gpu_launches": int(launches_all),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORK))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+"""
+fatiando_b200 -- the right-rectangular-prism potential-field forward model of
+fatiando/fatiando, rebuilt for NVIDIA B200 (sm_100a).
+
+Scope (one hot path, nothing else): ``fatiando.gravmag.prism`` and its native
+kernel ``_prism``, the prism meshes that feed it, and the dense sensitivity
+(Jacobian) build on top.  See DESIGN.md.
+
+* :mod:`fatiando_b200.prism`   -- drop-in for ``fatiando.gravmag.prism``
+* :mod:`fatiando_b200._prism`  -- drop-in for the Cython module ``_prism``
+* :mod:`fatiando_b200.mesher`  -- ``Prism``, ``PrismMesh``, ``PrismRelief``
+* :mod:`fatiando_b200.flatten` -- mesh -> SoA arrays
+* :mod:`fatiando_b200.partition` -- observation / prism sharding over GPUs
+* :mod:`fatiando_b200.gridder`, :mod:`~fatiando_b200.utils`,
+  :mod:`~fatiando_b200.constants` -- the support functions the path uses
+
+The compute library (``libfatiando_b200.so``, C ABI in
+``include/fatiando_b200.h``) is loaded lazily on first use; there is no CPU
+implementation behind it.
+"""
+from . import constants, gridder, mesher, utils          # noqa: F401
+from . import flatten, prism, _prism, partition          # noqa: F401
+from .mesher import Prism, PrismMesh, PrismRelief        # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,113 @@
+"""
+ctypes binding of libfatiando_b200.so (C ABI: include/fatiando_b200.h).
+
+The library is built in-tree by :mod:`fatiando_b200.build` (nvcc, sm_100a).
+There is no fallback of any kind: if the shared object is missing the import of
+the compute API raises, and if no CUDA device is usable every compute call
+raises ``RuntimeError`` with the library's own message.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfatiando_b200.so")
+
+OK, EINVAL, ECUDA, EPROP, EUNSUP = 0, -1, -2, -3, -4
+DEVICE_POINTERS, REFERENCE_ORDER, TRANSPOSED = 1, 2, 4
+
+FIELDS = ("potential", "gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz",
+          "gzz", "tf", "bx", "by", "bz")
+FIELD_ID = {name: i for i, name in enumerate(FIELDS)}
+GRAVITY_MASK, MAGNETIC_MASK = 0x03FF, 0x3C00
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_i64 = ctypes.c_int64
+_d = ctypes.c_double
+
+_PRISM_GRAVITY = [_dp, _dp, _dp, _i64] + [_d] * 7 + [_dp]
+_SIGNATURES = {
+    "fb200_abi_version": ([], ctypes.c_int),
+    "fb200_last_error": ([], ctypes.c_char_p),
+    "fb200_device_count": ([ctypes.POINTER(ctypes.c_int)], ctypes.c_int),
+    "fb200_device_info": ([ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
+                           ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64)], ctypes.c_int),
+    "fb200_model_create": ([ctypes.c_int, _i64] + [_dp] * 10 + [ctypes.POINTER(ctypes.c_void_p)],
+                           ctypes.c_int),
+    "fb200_model_destroy": ([ctypes.c_void_p], ctypes.c_int),
+    "fb200_model_size": ([ctypes.c_void_p], _i64),
+    "fb200_model_device": ([ctypes.c_void_p], ctypes.c_int),
+    "fb200_forward": ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64,
+                       ctypes.c_uint32, _dp, _dp, _dp, _dp, ctypes.c_void_p, _i64,
+                       ctypes.c_uint32], ctypes.c_int),
+    "fb200_jacobian": ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64,
+                        ctypes.c_int, _dp, _dp, _d, ctypes.c_void_p, _i64, ctypes.c_uint32],
+                       ctypes.c_int),
+    "fb200_set_default_device": ([ctypes.c_int], ctypes.c_int),
+    "fb200_prism_tf": ([_dp, _dp, _dp, _i64] + [_d] * 12 + [_dp], ctypes.c_int),
+    "fb200_prism_bx": ([_dp, _dp, _dp, _i64] + [_d] * 9 + [_dp], ctypes.c_int),
+    "fb200_prism_by": ([_dp, _dp, _dp, _i64] + [_d] * 9 + [_dp], ctypes.c_int),
+    "fb200_prism_bz": ([_dp, _dp, _dp, _i64] + [_d] * 9 + [_dp], ctypes.c_int),
+    "fb200_last_kernel_ms": ([ctypes.c_void_p, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int)],
+                             ctypes.c_int),
+    "fb200_fp64_peak": ([ctypes.c_int, _d, ctypes.POINTER(_d), ctypes.POINTER(_d)], ctypes.c_int),
+    "fb200_flush_l2": ([ctypes.c_int], ctypes.c_int),
+    "fb200_debug_math": ([ctypes.c_int, ctypes.c_int, _dp, _dp, _i64, _dp], ctypes.c_int),
+}
+for _name in ("potential", "gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz", "gzz"):
+    _SIGNATURES["fb200_prism_" + _name] = (_PRISM_GRAVITY, ctypes.c_int)
+
+_lib = None
+
+
+def lib():
+    """The loaded library (raises ImportError when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s is missing: build it with `python -m fatiando_b200.build` "
+                "(fatiando_b200 has no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = L
+    return _lib
+
+
+def last_error():
+    msg = lib().fb200_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc):
+    """Turn a C-ABI return code into the Python exception the API promises."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc in (EINVAL, EPROP, EUNSUP):
+        raise ValueError(msg)
+    raise RuntimeError("fatiando_b200 CUDA failure: " + msg)
+
+
+def dptr(a):
+    """Pointer to the data of a C-contiguous float64 array (or None)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    rc = lib().fb200_device_count(ctypes.byref(n))
+    return n.value if rc == OK else 0
+
+
+def require_device():
+    n = ctypes.c_int(0)
+    check(lib().fb200_device_count(ctypes.byref(n)))
+    return n.value

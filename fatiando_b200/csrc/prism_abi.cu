@@ -1,0 +1,732 @@
+// prism_abi.cu -- the C ABI of libfatiando_b200.so (include/fatiando_b200.h).
+//
+// Host-side plumbing only: model handles that own the SoA prism arrays in HBM
+// ("uploaded once"), staging of host point/result buffers, decomposition of a
+// requested field mask into the instantiated component sets, the prism-split
+// heuristic for small N, and CUDA-event timing.  All arithmetic lives in the
+// kernel translation units.  No entry point has a CPU compute path: if CUDA
+// is unusable they fail with FB200_ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fatiando_b200.h"
+#include "prism_fastmath.cuh"
+#include "prism_launch.h"
+#include "prism_masks.h"
+
+using namespace fb200;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess)                                                     \
+            return fail(FB200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// model handle
+// ---------------------------------------------------------------------------
+struct fb200_model {
+    int device = 0;
+    int sm_count = 148;
+    int64_t m = 0;
+    double *d_b[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *d_dens = nullptr;
+    double *d_mag[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // grow-only scratch
+    double *d_pts = nullptr;  size_t pts_cap = 0;     // 3*n staged points
+    double *d_out = nullptr;  size_t out_cap = 0;     // staged results
+    double *d_part = nullptr; size_t part_cap = 0;    // prism-split partials
+    double last_ms = 0.0;
+    int last_launches = 0;
+    std::mutex lock;   // one call at a time per handle
+};
+
+static int grow(double **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return FB200_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CK(cudaMalloc((void **)buf, need * sizeof(double)));
+    *cap = need;
+    return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// small kernels owned by this file
+// ---------------------------------------------------------------------------
+// out[out_row[c]*ld_out + l] = scale[c] * sum_s part[(s*nc + c)*ld + l], s ascending:
+// the fixed-order second stage of the prism split (reproducible run to run).
+struct ReduceArgs {
+    const double *part;
+    double *out;
+    int64_t n, ld, ld_out;
+    int nc, nsplit;
+    double scale[F_COUNT];
+    int out_row[F_COUNT];
+};
+
+__global__ void reduce_partials_kernel(const ReduceArgs a)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (l >= a.n) return;
+    double s = 0.0;
+    for (int k = 0; k < a.nsplit; ++k) s += a.part[((int64_t)k * a.nc + c) * a.ld + l];
+    a.out[(int64_t)a.out_row[c] * a.ld_out + l] = s * a.scale[c];
+}
+
+__global__ void fill_kernel(double *p, int64_t n, double v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// 8 independent DFMA chains per thread, everything in registers.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4,
+           x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void debug_math_kernel(int op, const double *a, const double *b, int64_t n, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = 0.0;
+    switch (op) {
+    case 0: r = fm::log_ratio(a[i], b[i]); break;
+    case 1: r = fm::atan_rhp(a[i], b[i]); break;
+    case 2: r = fm::div_fast(a[i], b[i]); break;
+    case 3: r = fm::root(a[i]); break;
+    case 4: r = sqrt(a[i]); break;
+    default: break;
+    }
+    out[i] = r;
+}
+
+// ---------------------------------------------------------------------------
+// housekeeping
+// ---------------------------------------------------------------------------
+extern "C" int fb200_abi_version(void) { return FB200_ABI_VERSION; }
+
+extern "C" const char *fb200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fb200_device_count(int *count)
+{
+    if (!count) return fail(FB200_EINVAL, "count is NULL");
+    *count = 0;
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FB200_ECUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = c;
+    if (c == 0) return fail(FB200_ECUDA, "no CUDA device visible");
+    return FB200_OK;
+}
+
+extern "C" int fb200_device_info(int device, char *name, int name_len, int *sm_count,
+                                 int64_t *total_mem_bytes)
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) {
+        std::strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = '\0';
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem_bytes) *total_mem_bytes = (int64_t)prop.totalGlobalMem;
+    return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+static int upload(double **dst, const double *src, int64_t m, int64_t m_pad, cudaStream_t s)
+{
+    CK(cudaMalloc((void **)dst, (size_t)m_pad * sizeof(double)));
+    CK(cudaMemsetAsync(*dst, 0, (size_t)m_pad * sizeof(double), s));
+    if (m > 0) CK(cudaMemcpyAsync(*dst, src, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
+    return FB200_OK;
+}
+
+extern "C" int fb200_model_destroy(fb200_model *model)
+{
+    if (!model) return FB200_OK;
+    DeviceGuard g(model->device);
+    for (double *p : model->d_b) if (p) cudaFree(p);
+    if (model->d_dens) cudaFree(model->d_dens);
+    for (double *p : model->d_mag) if (p) cudaFree(p);
+    if (model->d_pts) cudaFree(model->d_pts);
+    if (model->d_out) cudaFree(model->d_out);
+    if (model->d_part) cudaFree(model->d_part);
+    if (model->ev0) cudaEventDestroy(model->ev0);
+    if (model->ev1) cudaEventDestroy(model->ev1);
+    if (model->stream) cudaStreamDestroy(model->stream);
+    delete model;
+    return FB200_OK;
+}
+
+extern "C" int fb200_model_create(int device, int64_t m, const double *x1, const double *x2,
+                                  const double *y1, const double *y2, const double *z1,
+                                  const double *z2, const double *density, const double *mx,
+                                  const double *my, const double *mz, fb200_model **out)
+{
+    if (!out) return fail(FB200_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (m < 0) return fail(FB200_EINVAL, "negative prism count");
+    if (m > 0 && (!x1 || !x2 || !y1 || !y2 || !z1 || !z2))
+        return fail(FB200_EINVAL, "prism bound array is NULL");
+    const int nmag = (mx != nullptr) + (my != nullptr) + (mz != nullptr);
+    if (nmag != 0 && nmag != 3)
+        return fail(FB200_EINVAL, "mx, my, mz must be all NULL or all given");
+    int count = 0;
+    int rc = fb200_device_count(&count);
+    if (rc != FB200_OK) return rc;
+    if (device < 0 || device >= count) return fail(FB200_EINVAL, "device index out of range");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+
+    fb200_model *mod = new fb200_model();
+    mod->device = device;
+    mod->m = m;
+    cudaDeviceGetAttribute(&mod->sm_count, cudaDevAttrMultiProcessorCount, device);
+    const int64_t m_pad = std::max<int64_t>(TILE, (m + TILE - 1) / TILE * TILE);
+    const double *src[6] = {x1, x2, y1, y2, z1, z2};
+#define CKM(expr)                              \
+    do {                                       \
+        int rc_ = (expr);                      \
+        if (rc_ != FB200_OK) {                 \
+            std::string keep = g_err;          \
+            fb200_model_destroy(mod);          \
+            g_err = keep;                      \
+            return rc_;                        \
+        }                                      \
+    } while (0)
+    auto cuda_rc = [](cudaError_t e, const char *what) {
+        return e == cudaSuccess ? FB200_OK : fail(FB200_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    CKM(cuda_rc(cudaStreamCreateWithFlags(&mod->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+    CKM(cuda_rc(cudaEventCreate(&mod->ev0), "cudaEventCreate"));
+    CKM(cuda_rc(cudaEventCreate(&mod->ev1), "cudaEventCreate"));
+    for (int r = 0; r < 6; ++r) CKM(upload(&mod->d_b[r], src[r], m, m_pad, mod->stream));
+    if (density) CKM(upload(&mod->d_dens, density, m, m_pad, mod->stream));
+    if (nmag == 3) {
+        CKM(upload(&mod->d_mag[0], mx, m, m_pad, mod->stream));
+        CKM(upload(&mod->d_mag[1], my, m, m_pad, mod->stream));
+        CKM(upload(&mod->d_mag[2], mz, m, m_pad, mod->stream));
+    }
+    CKM(cuda_rc(cudaStreamSynchronize(mod->stream), "cudaStreamSynchronize"));
+#undef CKM
+    *out = mod;
+    return FB200_OK;
+}
+
+extern "C" int64_t fb200_model_size(const fb200_model *model) { return model ? model->m : -1; }
+extern "C" int fb200_model_device(const fb200_model *model) { return model ? model->device : -1; }
+
+extern "C" int fb200_last_kernel_ms(const fb200_model *model, double *ms, int *launches)
+{
+    if (!model) return fail(FB200_EINVAL, "model is NULL");
+    if (ms) *ms = model->last_ms;
+    if (launches) *launches = model->last_launches;
+    return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+static const uint32_t kGravitySets[] = {
+#define X(M) (M),
+    FB200_GRAVITY_SETS(X)
+#undef X
+};
+static const uint32_t kMagneticSets[] = {
+#define X(M) (M),
+    FB200_MAGNETIC_SETS(X)
+#undef X
+};
+
+// Greedy cover of `want` by instantiated sets: the largest subset first.
+template <size_t N>
+static std::vector<uint32_t> cover(uint32_t want, const uint32_t (&sets)[N])
+{
+    std::vector<uint32_t> res;
+    while (want) {
+        uint32_t best = 0;
+        for (uint32_t s : sets)
+            if ((s & ~want) == 0 && popc(s) > popc(best)) best = s;
+        res.push_back(best);
+        want &= ~best;
+    }
+    return res;
+}
+
+static void view_of(const fb200_model *mod, bool magnetic, ModelView *v)
+{
+    for (int r = 0; r < 6; ++r) v->b[r] = mod->d_b[r];
+    if (magnetic) {
+        for (int r = 0; r < 3; ++r) v->p[r] = mod->d_mag[r];
+    } else {
+        v->p[0] = mod->d_dens;
+        v->p[1] = v->p[2] = nullptr;
+    }
+    v->m = mod->m;
+}
+
+// One instantiated component set over all points; handles the prism split.
+static int run_set(fb200_model *mod, uint32_t set, uint32_t request, bool exact, bool allow_split,
+                   const double *d_xp, const double *d_yp, const double *d_zp, int64_t n,
+                   const double *override_p, const double *fvec, const double *scale,
+                   const double *init, double *d_out, int64_t ld_out)
+{
+    const bool magnetic = (set & MAGNETIC_MASK) != 0;
+    ForwardArgs a;
+    std::memset(&a, 0, sizeof(a));
+    view_of(mod, magnetic, &a.model);
+    a.xp = d_xp; a.yp = d_yp; a.zp = d_zp; a.n = n;
+    a.use_override = override_p != nullptr;
+    for (int r = 0; r < 3; ++r) a.override_p[r] = override_p ? override_p[magnetic ? r : 0] : 0.0;
+    for (int r = 0; r < 3; ++r) a.fvec[r] = fvec ? fvec[r] : 0.0;
+    a.init = init;
+    const int nc = popc(set);
+    int c = 0;
+    for (int f = 0; f < F_COUNT; ++f) {
+        if (!(set & bit(f))) continue;
+        const int row = popc(request & (bit(f) - 1));   // position among the requested fields
+        a.out_row[c] = row;
+        a.scale[c] = scale ? scale[row] : 1.0;
+        ++c;
+    }
+    // prism split: keep every SM busy when there are few points
+    const int64_t blocks_x = (n + FWD_THREADS - 1) / FWD_THREADS;
+    const int64_t tiles = (mod->m + TILE - 1) / TILE;
+    int64_t nsplit = 1;
+    if (allow_split && init == nullptr) {
+        const int64_t target = (int64_t)mod->sm_count * 20;
+        nsplit = std::min<int64_t>(std::max<int64_t>(1, (target + blocks_x - 1) / blocks_x), tiles);
+        nsplit = std::min<int64_t>(nsplit, 65535);
+    }
+    int64_t chunk = ((tiles + nsplit - 1) / nsplit) * TILE;
+    nsplit = (mod->m + chunk - 1) / chunk;
+    a.chunk = chunk;
+    a.nsplit = (int)nsplit;
+    auto launch = [&](const ForwardArgs &args) -> cudaError_t {
+        if (exact) return launch_forward_exact(set, args, mod->stream);
+        return magnetic ? launch_forward_fast_mag(set, args, mod->stream)
+                        : launch_forward_fast_grav(set, args, mod->stream);
+    };
+    if (nsplit == 1) {
+        a.out = d_out;
+        a.ld = ld_out;
+        CK(launch(a));
+        mod->last_launches += 1;
+        return FB200_OK;
+    }
+    const int64_t ld_p = (n + 31) / 32 * 32;
+    int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * nc * ld_p);
+    if (rc != FB200_OK) return rc;
+    a.out = mod->d_part;
+    a.ld = ld_p;
+    CK(launch(a));
+    ReduceArgs r;
+    std::memset(&r, 0, sizeof(r));
+    r.part = mod->d_part; r.out = d_out; r.n = n; r.ld = ld_p; r.ld_out = ld_out;
+    r.nc = nc; r.nsplit = (int)nsplit;
+    for (int k = 0; k < nc; ++k) { r.scale[k] = a.scale[k]; r.out_row[k] = a.out_row[k]; }
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
+    reduce_partials_kernel<<<grid, 256, 0, mod->stream>>>(r);
+    CK(cudaGetLastError());
+    mod->last_launches += 2;
+    return FB200_OK;
+}
+
+static int forward_impl(fb200_model *mod, const double *xp, const double *yp, const double *zp,
+                        int64_t n, uint32_t field_mask, const double *dens_override,
+                        const double *pmag_override, const double *fvec, const double *scale,
+                        const double *init, double *out, int64_t ld_out, uint32_t flags)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    if (n < 0) return fail(FB200_EINVAL, "negative point count");
+    if (field_mask == 0 || (field_mask & ~(GRAVITY_MASK | MAGNETIC_MASK)))
+        return fail(FB200_EINVAL, "invalid field mask");
+    if (n > 0 && (!xp || !yp || !zp || !out)) return fail(FB200_EINVAL, "NULL point or output array");
+    if (ld_out < n) return fail(FB200_EINVAL, "ld_out smaller than n");
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER))
+        return fail(FB200_EUNSUP, "unsupported flag for fb200_forward");
+    const uint32_t gmask = field_mask & GRAVITY_MASK, mmask = field_mask & MAGNETIC_MASK;
+    if (gmask && !mod->d_dens && !dens_override)
+        return fail(FB200_EPROP, "gravity field requested but the model holds no density");
+    if (mmask && !mod->d_mag[0] && !pmag_override)
+        return fail(FB200_EPROP, "magnetic field requested but the model holds no magnetization");
+    if ((mmask & bit(F_TF)) && !fvec)
+        return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
+    const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
+    const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
+    const int nreq = popc(field_mask);
+    if (n == 0) return FB200_OK;
+
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    mod->last_launches = 0;
+    mod->last_ms = 0.0;
+
+    const double *d_xp = xp, *d_yp = yp, *d_zp = zp, *d_init = init;
+    double *d_out = out;
+    int64_t ld = ld_out;
+    if (!on_device) {
+        const int64_t np = (n + 31) / 32 * 32;
+        int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3);
+        if (rc != FB200_OK) return rc;
+        rc = grow(&mod->d_out, &mod->out_cap, (size_t)np * nreq);
+        if (rc != FB200_OK) return rc;
+        CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+        CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+        CK(cudaMemcpyAsync(mod->d_pts + 2 * np, zp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+        d_xp = mod->d_pts; d_yp = mod->d_pts + np; d_zp = mod->d_pts + 2 * np;
+        d_out = mod->d_out;
+        ld = np;
+        if (init) {   // running sum starts from the caller's res (single field)
+            CK(cudaMemcpyAsync(d_out, init, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+            d_init = d_out;
+        }
+    }
+    if (mod->m == 0) {   // empty model: zeros (times scale), or init unchanged
+        if (!init) {
+            for (int c = 0; c < nreq; ++c) {
+                fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(d_out + (int64_t)c * ld, n, 0.0);
+                CK(cudaGetLastError());
+            }
+        }
+    } else {
+        CK(cudaEventRecord(mod->ev0, mod->stream));
+        if (gmask) {
+            for (uint32_t set : cover(gmask, kGravitySets)) {
+                int rc = run_set(mod, set, field_mask, exact, !exact, d_xp, d_yp, d_zp, n,
+                                 dens_override, fvec, scale, d_init, d_out, ld);
+                if (rc != FB200_OK) return rc;
+            }
+        }
+        if (mmask) {
+            for (uint32_t set : cover(mmask, kMagneticSets)) {
+                int rc = run_set(mod, set, field_mask, exact, !exact, d_xp, d_yp, d_zp, n,
+                                 pmag_override, fvec, scale, d_init, d_out, ld);
+                if (rc != FB200_OK) return rc;
+            }
+        }
+        CK(cudaEventRecord(mod->ev1, mod->stream));
+    }
+    if (!on_device) {
+        CK(cudaMemcpy2DAsync(out, (size_t)ld_out * 8, d_out, (size_t)ld * 8, (size_t)n * 8,
+                             (size_t)nreq, cudaMemcpyDeviceToHost, mod->stream));
+    }
+    CK(cudaStreamSynchronize(mod->stream));
+    if (mod->m > 0) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+        mod->last_ms = ms;
+    }
+    return FB200_OK;
+}
+
+extern "C" int fb200_forward(fb200_model *model, const double *xp, const double *yp,
+                             const double *zp, int64_t n, uint32_t field_mask,
+                             const double *dens_override, const double *pmag_override,
+                             const double *fvec, const double *scale, double *out,
+                             int64_t ld_out, uint32_t flags)
+{
+    return forward_impl(model, xp, yp, zp, n, field_mask, dens_override, pmag_override, fvec,
+                        scale, nullptr, out, ld_out, flags);
+}
+
+// ---------------------------------------------------------------------------
+// Jacobian
+// ---------------------------------------------------------------------------
+extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *yp,
+                              const double *zp, int64_t n, int field, const double *unit_prop,
+                              const double *fvec, double scale, double *out, int64_t ld,
+                              uint32_t flags)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    if (n < 0) return fail(FB200_EINVAL, "negative point count");
+    if (field < 0 || field >= F_COUNT) return fail(FB200_EINVAL, "invalid field id");
+    if (!unit_prop) return fail(FB200_EINVAL, "unit_prop is NULL");
+    if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_TRANSPOSED))
+        return fail(FB200_EUNSUP, "unsupported flag for fb200_jacobian");
+    const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
+    const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
+    const bool transposed = (flags & FB200_TRANSPOSED) != 0;
+    const int64_t m = mod->m;
+    if (n == 0 || m == 0) return FB200_OK;
+    if (!xp || !yp || !zp || !out) return fail(FB200_EINVAL, "NULL point or output array");
+    if (ld < (transposed ? n : m)) return fail(FB200_EINVAL, "ld smaller than the row length");
+    const bool magnetic = field >= F_TF;
+
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    mod->last_launches = 0;
+    mod->last_ms = 0.0;
+
+    JacobianArgs a;
+    std::memset(&a, 0, sizeof(a));
+    view_of(mod, magnetic, &a.model);
+    for (int r = 0; r < 3; ++r) a.unit_p[r] = magnetic ? unit_prop[r] : (r == 0 ? unit_prop[0] : 0.0);
+    for (int r = 0; r < 3; ++r) a.fvec[r] = fvec ? fvec[r] : 0.0;
+    a.scale = scale;
+    auto launch = [&](const JacobianArgs &args) -> cudaError_t {
+        return exact ? launch_jacobian_exact(field, transposed, args, mod->stream)
+                     : launch_jacobian_fast(field, transposed, args, mod->stream);
+    };
+    // points per launch: grid.y limit, and (host output) a bounded staging block
+    const int64_t max_rows_grid = (int64_t)65535 * JAC_TILE;
+    if (on_device) {
+        CK(cudaEventRecord(mod->ev0, mod->stream));
+        for (int64_t r0 = 0; r0 < n; r0 += max_rows_grid) {
+            const int64_t rb = std::min(max_rows_grid, n - r0);
+            a.xp = xp + r0; a.yp = yp + r0; a.zp = zp + r0; a.n = rb;
+            a.out = transposed ? out + r0 : out + r0 * ld;
+            a.ld = ld;
+            CK(launch(a));
+            mod->last_launches += 1;
+        }
+        CK(cudaEventRecord(mod->ev1, mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+        mod->last_ms = ms;
+        return FB200_OK;
+    }
+    // host output: stream the matrix back in row blocks of <= 256 MiB
+    const int64_t np = (n + 31) / 32 * 32;
+    int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3);
+    if (rc != FB200_OK) return rc;
+    CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+    CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+    CK(cudaMemcpyAsync(mod->d_pts + 2 * np, zp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+    int64_t rows = std::max<int64_t>(JAC_TILE, ((int64_t)(256ll << 20) / 8 / m) / JAC_TILE * JAC_TILE);
+    rows = std::min(rows, std::min(max_rows_grid, (n + JAC_TILE - 1) / JAC_TILE * JAC_TILE));
+    rc = grow(&mod->d_out, &mod->out_cap, (size_t)rows * m);
+    if (rc != FB200_OK) return rc;
+    double total_ms = 0.0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+        const int64_t rb = std::min(rows, n - r0);
+        a.xp = mod->d_pts + r0; a.yp = mod->d_pts + np + r0; a.zp = mod->d_pts + 2 * np + r0;
+        a.n = rb;
+        a.out = mod->d_out;
+        a.ld = transposed ? rb : m;
+        CK(cudaEventRecord(mod->ev0, mod->stream));
+        CK(launch(a));
+        CK(cudaEventRecord(mod->ev1, mod->stream));
+        mod->last_launches += 1;
+        if (!transposed)
+            CK(cudaMemcpy2DAsync(out + r0 * ld, (size_t)ld * 8, mod->d_out, (size_t)m * 8,
+                                 (size_t)m * 8, (size_t)rb, cudaMemcpyDeviceToHost, mod->stream));
+        else
+            CK(cudaMemcpy2DAsync(out + r0, (size_t)ld * 8, mod->d_out, (size_t)rb * 8,
+                                 (size_t)rb * 8, (size_t)m, cudaMemcpyDeviceToHost, mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+        total_ms += ms;
+    }
+    mod->last_ms = total_ms;
+    return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the reference's own FFI shape: one prism accumulated into res
+// ---------------------------------------------------------------------------
+static int g_default_device = 0;
+
+extern "C" int fb200_set_default_device(int device)
+{
+    int count = 0;
+    int rc = fb200_device_count(&count);
+    if (rc != FB200_OK) return rc;
+    if (device < 0 || device >= count) return fail(FB200_EINVAL, "device index out of range");
+    g_default_device = device;
+    return FB200_OK;
+}
+
+static int prism_accumulate(int field, const double *xp, const double *yp, const double *zp,
+                            int64_t n, double x1, double x2, double y1, double y2, double z1,
+                            double z2, const double *props, const double *fvec, double *res)
+{
+    if (n < 0) return fail(FB200_EINVAL, "negative point count");
+    if (n == 0) return FB200_OK;
+    if (!xp || !yp || !zp || !res) return fail(FB200_EINVAL, "NULL array");
+    const bool magnetic = field >= F_TF;
+    fb200_model *mod = nullptr;
+    int rc = fb200_model_create(g_default_device, 1, &x1, &x2, &y1, &y2, &z1, &z2,
+                                magnetic ? nullptr : props, magnetic ? props : nullptr,
+                                magnetic ? props + 1 : nullptr, magnetic ? props + 2 : nullptr, &mod);
+    if (rc != FB200_OK) return rc;
+    rc = forward_impl(mod, xp, yp, zp, n, bit(field), nullptr, nullptr, fvec, nullptr, res, res, n,
+                      FB200_REFERENCE_ORDER);
+    std::string keep = g_err;
+    fb200_model_destroy(mod);
+    g_err = keep;
+    return rc;
+}
+
+#define GRAVITY_ENTRY(name, F)                                                                  \
+    extern "C" int fb200_prism_##name(const double *xp, const double *yp, const double *zp,     \
+                                      int64_t n, double x1, double x2, double y1, double y2,    \
+                                      double z1, double z2, double density, double *res)        \
+    {                                                                                           \
+        return prism_accumulate(F, xp, yp, zp, n, x1, x2, y1, y2, z1, z2, &density, nullptr, res); \
+    }
+GRAVITY_ENTRY(potential, F_POT)
+GRAVITY_ENTRY(gx, F_GX)
+GRAVITY_ENTRY(gy, F_GY)
+GRAVITY_ENTRY(gz, F_GZ)
+GRAVITY_ENTRY(gxx, F_GXX)
+GRAVITY_ENTRY(gxy, F_GXY)
+GRAVITY_ENTRY(gxz, F_GXZ)
+GRAVITY_ENTRY(gyy, F_GYY)
+GRAVITY_ENTRY(gyz, F_GYZ)
+GRAVITY_ENTRY(gzz, F_GZZ)
+#undef GRAVITY_ENTRY
+
+extern "C" int fb200_prism_tf(const double *xp, const double *yp, const double *zp, int64_t n,
+                              double x1, double x2, double y1, double y2, double z1, double z2,
+                              double mx, double my, double mz, double fx, double fy, double fz,
+                              double *res)
+{
+    const double m[3] = {mx, my, mz}, f[3] = {fx, fy, fz};
+    return prism_accumulate(F_TF, xp, yp, zp, n, x1, x2, y1, y2, z1, z2, m, f, res);
+}
+
+#define MAGNETIC_ENTRY(name, F)                                                                 \
+    extern "C" int fb200_prism_##name(const double *xp, const double *yp, const double *zp,     \
+                                      int64_t n, double x1, double x2, double y1, double y2,    \
+                                      double z1, double z2, double mx, double my, double mz,    \
+                                      double *res)                                              \
+    {                                                                                           \
+        const double m[3] = {mx, my, mz};                                                       \
+        return prism_accumulate(F, xp, yp, zp, n, x1, x2, y1, y2, z1, z2, m, nullptr, res);     \
+    }
+MAGNETIC_ENTRY(bx, F_BX)
+MAGNETIC_ENTRY(by, F_BY)
+MAGNETIC_ENTRY(bz, F_BZ)
+#undef MAGNETIC_ENTRY
+
+// ---------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------
+extern "C" int fb200_fp64_peak(int device, double seconds, double *burst_tflops,
+                               double *sustained_tflops)
+{
+    int count = 0;
+    int rc = fb200_device_count(&count);
+    if (rc != FB200_OK) return rc;
+    if (device < 0 || device >= count) return fail(FB200_EINVAL, "device index out of range");
+    DeviceGuard g(device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 2048;
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
+    for (int w = 0; w < 3; ++w) fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    CK(cudaDeviceSynchronize());
+    double best = 0.0, total_ms = 0.0, total_flop = 0.0;
+    while (total_ms < seconds * 1e3) {
+        CK(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::max(best, flop / (ms * 1e-3) / 1e12);
+        total_ms += ms;
+        total_flop += flop;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (burst_tflops) *burst_tflops = best;
+    if (sustained_tflops) *sustained_tflops = total_flop / (total_ms * 1e-3) / 1e12;
+    return FB200_OK;
+}
+
+extern "C" int fb200_flush_l2(int device)
+{
+    static double *bufs[64] = {nullptr};
+    if (device < 0 || device >= 64) return fail(FB200_EINVAL, "device index out of range");
+    DeviceGuard g(device);
+    const size_t bytes = (size_t)256 << 20;   // 2x the 126 MB L2
+    if (!bufs[device]) CK(cudaMalloc((void **)&bufs[device], bytes));
+    CK(cudaMemset(bufs[device], 0, bytes));
+    CK(cudaDeviceSynchronize());
+    return FB200_OK;
+}
+
+// op: 0 log_ratio(a, b), 1 atan_rhp(im = a, re = b), 2 div_fast(a, b), 3 root(a), 4 sqrt(a).
+// Host arrays; exists so that tests can pin the device math against mpmath/numpy.
+extern "C" int fb200_debug_math(int device, int op, const double *a, const double *b, int64_t n,
+                                double *out)
+{
+    if (n <= 0) return FB200_OK;
+    if (!a || !b || !out) return fail(FB200_EINVAL, "NULL array");
+    DeviceGuard g(device);
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)n * 3 * sizeof(double)));
+    CK(cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d + n, b, (size_t)n * 8, cudaMemcpyHostToDevice));
+    debug_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(op, d, d + n, n, d + 2 * n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return FB200_OK;
+}

@@ -71,11 +71,13 @@ struct ForwardArgs {
     // prism split: block (bx, by) handles prisms [by*chunk, min(m,(by+1)*chunk))
     int64_t chunk;
     int nsplit;
-    // nsplit == 1: out[c*ld + l] = (init? init[l] : 0 ... ) scaled; else partials
-    double *out;             // [ncomp][ld]  (final)  or [nsplit][ncomp][ld] (partials)
+    // nsplit == 1: out[out_row[c]*ld + l] = acc[c] * scale[c]
+    // nsplit  > 1: out is scratch, out[(split*ncomp + c)*ld + l] = acc[c] (unscaled)
+    double *out;
     int64_t ld;
     const double *init;      // optional starting value of the running sum (ncomp == 1)
-    double scale[F_COUNT];   // per requested component, in ascending field order
+    double scale[F_COUNT];   // per component of this launch, ascending field order
+    int out_row[F_COUNT];    // destination row of each component
 };
 
 }  // namespace fb200

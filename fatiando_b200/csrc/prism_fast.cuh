@@ -13,7 +13,7 @@
 //     tf/bx/by/bz, which use the unshifted kernels (:94-99).
 // They only matter when a coordinate difference is exactly zero; those pairs
 // take a short predicated fix-up block.  Differences so small that their
-// squares underflow (|d| < 2^-500, never seen in metres) fall back to the
+// squares underflow (|d| < 2^-480, never seen in metres) fall back to the
 // reference-order evaluator for that pair.
 #pragma once
 #include "prism_common.cuh"
@@ -152,9 +152,24 @@ struct AtanFam {
     }
 };
 
-// |d| < 2^-500 (zero, denormal or so small that d*d underflows): exponent test
-// on the ALU pipe.
-FB_HD bool tiny_or_zero(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x20b00000; }
+// Rare pairs whose squared differences underflow: reference-order evaluation,
+// kept out of line so the hot loop stays small.
+template <uint32_t MASK>
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+static
+#endif
+void pair_slow(double (&acc)[popc(MASK)], double xp, double yp, double zp, double x1, double x2,
+               double y1, double y2, double z1, double z2, double p0, double p1, double p2,
+               const double (&f)[3])
+{
+    pair_exact<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
+}
+
+// |d| < 2^-480 (zero, denormal, or so small that d*d leaves the range of the
+// branch-free root): exponent test on the ALU pipe.
+FB_HD bool tiny_or_zero(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
 
 template <uint32_t MASK>
 FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
@@ -193,6 +208,24 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
     const double XX[2] = {mul(X[0], X[0]), mul(X[1], X[1])};
     const double YY[2] = {mul(Y[0], Y[0]), mul(Y[1], Y[1])};
     const double ZZ[2] = {mul(Z[0], Z[0]), mul(Z[1], Z[1])};
+    // exact-zero / underflow detection (ALU pipe); the common case skips both
+    // fix-up blocks below
+    const bool tx[2] = {tiny_or_zero(X[0]), tiny_or_zero(X[1])};
+    const bool ty[2] = {tiny_or_zero(Y[0]), tiny_or_zero(Y[1])};
+    const bool tz[2] = {tiny_or_zero(Z[0]), tiny_or_zero(Z[1])};
+    const bool special = tx[0] | tx[1] | ty[0] | ty[1] | tz[0] | tz[1];
+    bool zx[2] = {false, false}, zy[2] = {false, false}, zz[2] = {false, false};
+    if (special) {
+        zx[0] = X[0] == 0.0; zx[1] = X[1] == 0.0;
+        zy[0] = Y[0] == 0.0; zy[1] = Y[1] == 0.0;
+        zz[0] = Z[0] == 0.0; zz[1] = Z[1] == 0.0;
+        if ((tx[0] & !zx[0]) | (tx[1] & !zx[1]) | (ty[0] & !zy[0]) | (ty[1] & !zy[1]) |
+            (tz[0] & !zz[0]) | (tz[1] & !zz[1])) {
+            // squares underflow: evaluate this pair the reference's way
+            pair_slow<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
+            return;
+        }
+    }
     double r[8];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -200,7 +233,11 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
         for (int i = 0; i < 2; ++i) {
             const double sxy = add(XX[i], YY[j]);        // (dx**2 + dy**2) + dz**2
 #pragma unroll
-            for (int k = 0; k < 2; ++k) r[k * 4 + j * 2 + i] = root(add(sxy, ZZ[k]));
+            for (int k = 0; k < 2; ++k) {
+                const double r2 = add(sxy, ZZ[k]);
+                // on a vertex r2 == 0 and the branch-free root would give NaN
+                r[k * 4 + j * 2 + i] = (special && zx[i] && zy[j] && zz[k]) ? 0.0 : root(r2);
+            }
         }
 
     // ---- arguments, with the reference's roundings -------------------------
@@ -228,19 +265,7 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
 
     // ---- exact-zero differences: the reference's special cases --------------
     double ex_xy = 0.0, ex_xz = 0.0, ex_yz = 0.0;   // shifted-r terms of gxy, gxz, gyz
-    const bool tx[2] = {tiny_or_zero(X[0]), tiny_or_zero(X[1])};
-    const bool ty[2] = {tiny_or_zero(Y[0]), tiny_or_zero(Y[1])};
-    const bool tz[2] = {tiny_or_zero(Z[0]), tiny_or_zero(Z[1])};
-    if (tx[0] | tx[1] | ty[0] | ty[1] | tz[0] | tz[1]) {
-        const bool zx[2] = {X[0] == 0.0, X[1] == 0.0};
-        const bool zy[2] = {Y[0] == 0.0, Y[1] == 0.0};
-        const bool zz[2] = {Z[0] == 0.0, Z[1] == 0.0};
-        if ((tx[0] & !zx[0]) | (tx[1] & !zx[1]) | (ty[0] & !zy[0]) | (ty[1] & !zy[1]) |
-            (tz[0] & !zz[0]) | (tz[1] & !zz[1])) {
-            // squares underflow: evaluate this pair the reference's way
-            pair_exact<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
-            return;
-        }
+    if (special) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int i = c & 1, j = (c >> 1) & 1, k = c >> 2;

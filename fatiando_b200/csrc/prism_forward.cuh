@@ -63,7 +63,8 @@ forward_kernel(const ForwardArgs a)
     if (!active) return;
     if (a.nsplit == 1) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) a.out[(int64_t)c * a.ld + l] = acc[c] * a.scale[c];
+        for (int c = 0; c < NC; ++c)
+            a.out[(int64_t)a.out_row[c] * a.ld + l] = acc[c] * a.scale[c];
     } else {
         double *part = a.out + (int64_t)blockIdx.y * NC * a.ld;
 #pragma unroll

@@ -1,0 +1,115 @@
+// prism_jacobian.cuh -- the sensitivity-matrix (Jacobian) tile writers (K3).
+//
+// Replaces the per-cell loop jac[:, q] = prism.<field>(x, y, z, [cell_q], dens=1)
+// of the reference's inversion paths (eqlayer.py:108-111 layout;
+// harvester.py:720-724, imaging.py:116-117 call pattern).  Every entry is an
+// independent 8-corner sum started from 0.0 and multiplied by the unit scale,
+// exactly what one reference call returns for one cell.
+//
+// Two mappings, chosen so that the fp64 stores of a warp are contiguous:
+//   * C-order (ndata, nparams): lane <-> prism (bounds in registers), the block
+//     walks a tile of points broadcast from shared memory; a warp store covers
+//     32 consecutive doubles of one row (2 full 128-byte lines).
+//   * transposed (nparams, ndata), the imaging.py layout: lane <-> point,
+//     prisms broadcast from shared memory.
+// Stores are streaming (st.global.cs): the matrix is written once and read by
+// a later consumer, it must not evict the prism/point tiles from L2.
+// Arithmetic per entry ~330-1000 FP64 instructions vs 8 bytes stored: the kernel
+// is FP64-pipe-bound by >10x (DESIGN.md "Rooflines"); the DRAM-write rate is
+// reported as a secondary counter.
+#pragma once
+#include "prism_common.cuh"
+
+namespace fb200 {
+
+constexpr int JAC_THREADS = 128;
+constexpr int JAC_TILE = 128;    // points (or prisms) staged per block
+
+struct JacobianArgs {
+    ModelView model;
+    const double *xp, *yp, *zp;
+    int64_t n;
+    double unit_p[3];    // unit density, or unit magnetization vector
+    double fvec[3];
+    double scale;
+    double *out;
+    int64_t ld;
+};
+
+// C-order: out[l * ld + q]
+template <uint32_t MASK, class Eval>
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobian_kernel(const JacobianArgs a)
+{
+    static_assert(popc(MASK) == 1, "one field per Jacobian");
+    __shared__ double pts[3][JAC_TILE];
+    int64_t q = (int64_t)blockIdx.x * JAC_THREADS + threadIdx.x;
+    const bool active = q < a.model.m;
+    if (!active) q = a.model.m - 1;
+    const double x1 = a.model.b[0][q], x2 = a.model.b[1][q], y1 = a.model.b[2][q],
+                 y2 = a.model.b[3][q], z1 = a.model.b[4][q], z2 = a.model.b[5][q];
+    const double f[3] = {a.fvec[0], a.fvec[1], a.fvec[2]};
+    const double p0 = a.unit_p[0], p1 = a.unit_p[1], p2 = a.unit_p[2];
+    const int64_t l0 = (int64_t)blockIdx.y * JAC_TILE;
+    const int cnt = (a.n - l0 < JAC_TILE) ? (int)(a.n - l0) : JAC_TILE;
+    for (int idx = threadIdx.x; idx < cnt; idx += JAC_THREADS) {
+        pts[0][idx] = a.xp[l0 + idx];
+        pts[1][idx] = a.yp[l0 + idx];
+        pts[2][idx] = a.zp[l0 + idx];
+    }
+    __syncthreads();
+    double *row = a.out + l0 * a.ld + q;
+#pragma unroll 1
+    for (int r = 0; r < cnt; ++r) {
+        double acc[1] = {0.0};
+        Eval::template pair<MASK>(acc, pts[0][r], pts[1][r], pts[2][r], x1, x2, y1, y2, z1, z2,
+                                  p0, p1, p2, f);
+        if (active) __stcs(row + (int64_t)r * a.ld, acc[0] * a.scale);
+    }
+}
+
+// transposed: out[q * ld + l]
+template <uint32_t MASK, class Eval>
+__global__ void __launch_bounds__(JAC_THREADS)
+jacobian_t_kernel(const JacobianArgs a)
+{
+    static_assert(popc(MASK) == 1, "one field per Jacobian");
+    __shared__ double sp[6][JAC_TILE];
+    int64_t l = (int64_t)blockIdx.x * JAC_THREADS + threadIdx.x;
+    const bool active = l < a.n;
+    if (!active) l = a.n - 1;
+    const double xp = a.xp[l], yp = a.yp[l], zp = a.zp[l];
+    const double f[3] = {a.fvec[0], a.fvec[1], a.fvec[2]};
+    const double p0 = a.unit_p[0], p1 = a.unit_p[1], p2 = a.unit_p[2];
+    const int64_t q0 = (int64_t)blockIdx.y * JAC_TILE;
+    const int cnt = (a.model.m - q0 < JAC_TILE) ? (int)(a.model.m - q0) : JAC_TILE;
+    for (int idx = threadIdx.x; idx < cnt; idx += JAC_THREADS)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) sp[r][idx] = a.model.b[r][q0 + idx];
+    __syncthreads();
+    double *col = a.out + q0 * a.ld + l;
+#pragma unroll 1
+    for (int q = 0; q < cnt; ++q) {
+        double acc[1] = {0.0};
+        Eval::template pair<MASK>(acc, xp, yp, zp, sp[0][q], sp[1][q], sp[2][q], sp[3][q],
+                                  sp[4][q], sp[5][q], p0, p1, p2, f);
+        if (active) __stcs(col + (int64_t)q * a.ld, acc[0] * a.scale);
+    }
+}
+
+template <uint32_t MASK, class Eval>
+inline cudaError_t launch_jacobian_t(const JacobianArgs &a, bool transposed, cudaStream_t stream)
+{
+    if (!transposed) {
+        dim3 grid((unsigned)((a.model.m + JAC_THREADS - 1) / JAC_THREADS),
+                  (unsigned)((a.n + JAC_TILE - 1) / JAC_TILE));
+        jacobian_kernel<MASK, Eval><<<grid, JAC_THREADS, 0, stream>>>(a);
+    } else {
+        dim3 grid((unsigned)((a.n + JAC_THREADS - 1) / JAC_THREADS),
+                  (unsigned)((a.model.m + JAC_TILE - 1) / JAC_TILE));
+        jacobian_t_kernel<MASK, Eval><<<grid, JAC_THREADS, 0, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fb200

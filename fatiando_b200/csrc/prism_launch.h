@@ -1,0 +1,17 @@
+// prism_launch.h -- host-side entry points of the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "prism_common.cuh"
+#include "prism_jacobian.cuh"
+
+namespace fb200 {
+
+// Each returns cudaErrorInvalidValue when `mask` is not one of the instantiated
+// component sets of prism_masks.h (callers decompose requests first).
+cudaError_t launch_forward_exact(uint32_t mask, const ForwardArgs &a, cudaStream_t s);      // fwd_exact.cu
+cudaError_t launch_forward_fast_grav(uint32_t mask, const ForwardArgs &a, cudaStream_t s);  // fwd_fast_grav.cu
+cudaError_t launch_forward_fast_mag(uint32_t mask, const ForwardArgs &a, cudaStream_t s);   // fwd_fast_mag.cu
+cudaError_t launch_jacobian_exact(int field, bool transposed, const JacobianArgs &a, cudaStream_t s);  // jac_exact.cu
+cudaError_t launch_jacobian_fast(int field, bool transposed, const JacobianArgs &a, cudaStream_t s);   // jac_fast.cu
+
+}  // namespace fb200

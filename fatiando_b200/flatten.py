@@ -1,0 +1,200 @@
+"""
+The mesh flattener: any "list of prisms" -> SoA arrays ready for upload.
+
+The reference walks its models one ``Prism`` object at a time
+(prism.py:131-141; ``PrismMesh.__getitem__`` mesh.py:617-636,
+``PrismRelief.__getitem__`` mesh.py:442-458), about 3-7 microseconds of Python
+per cell and per field call.  Here a whole model becomes six bound arrays plus
+property arrays in one vectorised pass.  The coordinate expressions are the
+reference's own, evaluated element-wise in float64, so every bound is the very
+same double the reference would hand to its kernel:
+
+* PrismMesh:   ``x1 = bounds[0] + dx*i``, ``x2 = x1 + dx``  (mesh.py:629-634)
+* PrismRelief: ``x1 = xc - 0.5*dx`` ..., z ordered against ``ref`` (:447-456)
+
+Skipping rules (prism.py:132, :647-649): ``None`` entries (masked cells) are
+always dropped; cells lacking the required property are dropped unless an
+override (``dens=`` / ``pmag=``) is given, in which case every non-``None`` cell
+counts.  Order is preserved -- it is the summation order.
+"""
+import numpy as np
+
+BOUND_NAMES = ('x1', 'x2', 'y1', 'y2', 'z1', 'z2')
+
+
+class FlatModel(object):
+    """
+    SoA view of a prism model.
+
+    * bounds : list of six float64 arrays (x1, x2, y1, y2, z1, z2), length m
+    * density : float64 array (m,) or None
+    * magnetization : float64 array (m, 3) or None
+    * index : int64 array (m,), position of each kept prism in the input
+    * total : number of entries of the input (kept + dropped)
+    """
+
+    def __init__(self, bounds, density, magnetization, index, total):
+        self.bounds = [np.ascontiguousarray(b, dtype=np.float64) for b in bounds]
+        self.density = None if density is None else np.ascontiguousarray(density, dtype=np.float64)
+        self.magnetization = (None if magnetization is None
+                              else np.ascontiguousarray(magnetization, dtype=np.float64))
+        self.index = np.ascontiguousarray(index, dtype=np.int64)
+        self.total = int(total)
+
+    @property
+    def size(self):
+        return int(self.bounds[0].size)
+
+    def extent(self):
+        """Largest absolute coordinate and smallest non-zero edge (for the
+        fast-path range guard)."""
+        if self.size == 0:
+            return 0.0, np.inf
+        big = max(float(np.max(np.abs(b))) for b in self.bounds)
+        edges = np.concatenate([np.abs(self.bounds[1] - self.bounds[0]),
+                                np.abs(self.bounds[3] - self.bounds[2]),
+                                np.abs(self.bounds[5] - self.bounds[4])])
+        edges = edges[edges > 0]
+        return big, (float(edges.min()) if edges.size else np.inf)
+
+
+def _is_scalar_property(value):
+    # the reference's test (prism.py:651): a Python float or int
+    # (numpy.float64 is a float subclass and counts)
+    return isinstance(value, (float, int))
+
+
+def _is_prism_mesh(obj):
+    return (all(hasattr(obj, a) for a in ('bounds', 'shape', 'dims', 'mask', 'props', 'size'))
+            and getattr(getattr(obj, 'celltype', None), '__name__', '') == 'Prism')
+
+
+def _is_prism_relief(obj):
+    return all(hasattr(obj, a) for a in ('ref', 'dx', 'dy', 'x', 'y', 'z', 'props', 'size'))
+
+
+def _mesh_bounds(mesh):
+    nz, ny, nx = mesh.shape
+    dx, dy, dz = (float(d) for d in mesh.dims)
+    b = mesh.bounds
+    i = np.arange(nx, dtype=np.float64)
+    j = np.arange(ny, dtype=np.float64)
+    k = np.arange(nz, dtype=np.float64)
+    x1 = float(b[0]) + dx * i
+    y1 = float(b[2]) + dy * j
+    z1 = float(b[4]) + dz * k
+    x2, y2, z2 = x1 + dx, y1 + dy, z1 + dz
+    shape = (nz, ny, nx)
+    full = lambda a, axis: np.broadcast_to(
+        a.reshape([-1 if ax == axis else 1 for ax in range(3)]), shape).ravel()
+    return [full(x1, 2), full(x2, 2), full(y1, 1), full(y2, 1), full(z1, 0), full(z2, 0)]
+
+
+def _relief_bounds(relief):
+    x = np.asarray(relief.x, dtype=np.float64)
+    y = np.asarray(relief.y, dtype=np.float64)
+    z = np.asarray(relief.z, dtype=np.float64)
+    dx, dy, ref = float(relief.dx), float(relief.dy), float(relief.ref)
+    above = z <= ref
+    return [x - 0.5 * dx, x + 0.5 * dx, y - 0.5 * dy, y + 0.5 * dy,
+            np.where(above, z, ref), np.where(above, ref, z)]
+
+
+def _property_arrays(props, size):
+    """(density or None, magnetization (m,3)/(m,) or None, needs_generic)"""
+    dens = mag = None
+    if 'density' in props:
+        dens = np.asarray(props['density'])
+        if dens.dtype == object or dens.shape != (size,):
+            return None, None, True
+        dens = dens.astype(np.float64)
+    if 'magnetization' in props:
+        mag = np.asarray(props['magnetization'])
+        if mag.dtype == object or mag.shape not in ((size,), (size, 3)):
+            return None, None, True
+        mag = mag.astype(np.float64)
+    return dens, mag, False
+
+
+def flatten(prisms, prop=None, override=False, fvec=None):
+    """
+    Flatten ``prisms`` for a field that needs physical property ``prop``.
+
+    * prop : ``'density'``, ``'magnetization'`` or ``None`` (bounds only)
+    * override : a ``dens=`` / ``pmag=`` value replaces the property, so cells
+      without it are kept (prism.py:132-137)
+    * fvec : direction cosines of the inducing field; scalar magnetizations are
+      expanded to ``mag * fvec`` like prism.py:650-653 (total-field anomaly
+      only -- without ``fvec`` a scalar magnetization is an error, as it is
+      for ``bx, by, bz`` in the reference, prism.py:702)
+    """
+    bounds = dens = mag = keep = None
+    total = None
+    if _is_prism_mesh(prisms) or _is_prism_relief(prisms):
+        total = int(prisms.size)
+        dens, mag, generic = _property_arrays(prisms.props, total)
+        if not generic:
+            bounds = _mesh_bounds(prisms) if _is_prism_mesh(prisms) else _relief_bounds(prisms)
+            keep = np.ones(total, dtype=bool)
+            mask = getattr(prisms, 'mask', None)
+            if mask is not None and len(mask):
+                keep[np.asarray(mask, dtype=np.int64)] = False
+            if prop is not None and not override and prop not in prisms.props:
+                keep[:] = False
+    if bounds is None:
+        return _flatten_generic(prisms, prop, override, fvec)
+    index = np.nonzero(keep)[0]
+    if index.size != total:
+        bounds = [b[index] for b in bounds]
+        dens = None if dens is None else dens[index]
+        mag = None if mag is None else mag[index]
+    if override:
+        dens = mag = None
+    if prop != 'density':
+        dens = None
+    if prop != 'magnetization':
+        mag = None
+    if mag is not None and mag.ndim == 1:
+        mag = _expand_scalar_magnetization(mag, fvec)
+    return FlatModel(bounds, dens, mag, index, total)
+
+
+def _expand_scalar_magnetization(values, fvec):
+    if fvec is None:
+        raise TypeError("the 'magnetization' property must be a 3-component vector")
+    fx, fy, fz = fvec
+    values = np.asarray(values, dtype=np.float64)
+    return np.stack([values * fx, values * fy, values * fz], axis=1)
+
+
+def _flatten_generic(prisms, prop, override, fvec):
+    rows, dens, mag, index = [], [], [], []
+    total = 0
+    for pos, p in enumerate(prisms):
+        total = pos + 1
+        if p is None:
+            continue
+        if prop is not None and not override and prop not in p.props:
+            continue
+        rows.append((float(p.x1), float(p.x2), float(p.y1), float(p.y2),
+                     float(p.z1), float(p.z2)))
+        index.append(pos)
+        if override or prop is None:
+            continue
+        value = p.props[prop]
+        if prop == 'density':
+            dens.append(float(value))
+        elif _is_scalar_property(value):
+            if fvec is None:
+                raise TypeError("the 'magnetization' property must be a 3-component vector")
+            mag.append((value * fvec[0], value * fvec[1], value * fvec[2]))
+        else:
+            mx, my, mz = value
+            mag.append((float(mx), float(my), float(mz)))
+    arr = np.array(rows, dtype=np.float64).reshape(-1, 6)
+    bounds = [np.ascontiguousarray(arr[:, c]) for c in range(6)]
+    return FlatModel(bounds,
+                     np.array(dens, dtype=np.float64) if (prop == 'density' and not override) else None,
+                     (np.array(mag, dtype=np.float64).reshape(-1, 3)
+                      if (prop == 'magnetization' and not override) else None),
+                     np.array(index, dtype=np.int64), total)

@@ -1,0 +1,465 @@
+r"""
+Potential fields of the 3D right rectangular prism, computed on a B200.
+
+Drop-in for ``fatiando.gravmag.prism`` (reference: fatiando/gravmag/prism.py):
+the same twenty functions with the same signatures, conventions and units.
+
+.. note:: All input units are SI.  Output is in conventional units: SI for the
+    gravitational potential, mGal for gravity, Eotvos for gravity gradients, nT
+    for magnetic fields.
+
+.. note:: The coordinate system is x -> North, y -> East and z -> Down.
+
+**Gravity** (Nagy et al., 2000): :func:`potential`, :func:`gx`, :func:`gy`,
+:func:`gz`, :func:`gxx`, :func:`gxy`, :func:`gxz`, :func:`gyy`, :func:`gyz`,
+:func:`gzz`.  Like the reference, ``gxy``, ``gxz`` and ``gyz`` move the
+computation point slightly when it is aligned with a prism edge on the bottom,
+east and north side (prism.py "warning", _prism.pyx:327-330).
+
+**Magnetic** (Bhattacharyya, 1964): :func:`tf`, :func:`bx`, :func:`by`,
+:func:`bz`.
+
+**Auxiliary**: :func:`kernelxx` ... :func:`kernelzz`, the second derivatives of
+:math:`\int\int\int 1/r`.
+
+**What is different underneath.**  The reference calls a scalar C loop once per
+prism and per field.  Here the model is flattened once into SoA arrays
+(:mod:`fatiando_b200.flatten`), uploaded to HBM, and a fused CUDA kernel
+evaluates *all* requested components of *all* prisms in one pass.  Extras that
+the reference does not have, built on the same kernels:
+
+* :func:`fields` -- several components in one pass (shares the per-corner work);
+* :func:`jacobian` -- the dense sensitivity matrix, one column per cell;
+* :class:`Model` -- upload a model once, evaluate many times.
+
+There is no CPU implementation in this package: without the CUDA library or a
+GPU these functions raise.
+"""
+import ctypes
+
+import numpy
+
+from . import _lib, utils
+from .constants import G, SI2EOTVOS, CM, T2NT, SI2MGAL
+from .flatten import FlatModel, flatten
+
+GRAVITY_FIELDS = ('potential', 'gx', 'gy', 'gz', 'gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz')
+MAGNETIC_FIELDS = ('tf', 'bx', 'by', 'bz')
+
+# Coordinates larger than this are evaluated in reference order (the products
+# of the collapsed corner sums of the fast path would leave the double range).
+FAST_PATH_MAX_COORD = 1e15
+
+
+def unit_scale(field):
+    """The unit factor the reference multiplies each field by."""
+    if field == 'potential':
+        return G                    # prism.py:142
+    if field in ('gx', 'gy', 'gz'):
+        return G * SI2MGAL          # prism.py:190, :238, :286
+    if field in GRAVITY_FIELDS:
+        return G * SI2EOTVOS        # prism.py:334 ... :598
+    if field in MAGNETIC_FIELDS:
+        return CM * T2NT            # prism.py:661, :707, :753, :799
+    raise ValueError("unknown field '%s'" % field)
+
+
+def _check_points(xp, yp, zp, what):
+    # prism.py:127-128 ("...same length!") and :691-692 ("...same shape!")
+    if xp.shape != yp.shape or xp.shape != zp.shape:
+        raise ValueError("Input arrays xp, yp, and zp must have same %s!" % what)
+
+
+def _as_points(a):
+    # the reference kernel takes float64, 1-D buffers and nothing else
+    # (_prism.pyx:72-77): keep that contract, copy only for strides
+    if not isinstance(a, numpy.ndarray):
+        raise AttributeError("'%s' object has no attribute 'shape'" % type(a).__name__)
+    if a.dtype != numpy.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'float64' but got '%s'" % a.dtype)
+    if a.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (expected 1, got %d)" % a.ndim)
+    return numpy.ascontiguousarray(a)
+
+
+def _max_abs(*arrays):
+    return max([float(numpy.max(numpy.abs(a))) for a in arrays if a.size] + [0.0])
+
+
+class Model(object):
+    """
+    A prism model resident in GPU memory ("uploaded once").
+
+    * prisms : list of prisms, ``PrismMesh``, ``PrismRelief`` (this package's
+      or the reference's) or a :class:`~fatiando_b200.flatten.FlatModel`
+    * prop : ``'density'``, ``'magnetization'`` or ``None``; which physical
+      property the model carries.  With ``None`` only overrides
+      (``dens=`` / ``pmag=``) and Jacobians can be evaluated.
+    * keep_all : keep cells lacking ``prop`` (what an override needs,
+      prism.py:132-137)
+    * fvec : inducing-field direction, to expand scalar magnetizations
+    * device : CUDA device index
+
+    Use as a context manager or call :meth:`close`.
+    """
+
+    def __init__(self, prisms, prop='density', keep_all=False, fvec=None, device=0):
+        flat = prisms if isinstance(prisms, FlatModel) else \
+            flatten(prisms, prop, override=keep_all, fvec=fvec)
+        self.flat = flat
+        self.device = device
+        self.size = flat.size
+        self.max_coord, self.min_edge = flat.extent()
+        self._handle = ctypes.c_void_p()
+        lib = _lib.lib()
+        mag = flat.magnetization
+        cols = [None, None, None] if mag is None else \
+            [numpy.ascontiguousarray(mag[:, c]) for c in range(3)]
+        _lib.check(lib.fb200_model_create(
+            device, flat.size, *[_lib.dptr(b) for b in flat.bounds],
+            _lib.dptr(flat.density), *[_lib.dptr(c) for c in cols],
+            ctypes.byref(self._handle)))
+
+    # -- lifetime ----------------------------------------------------------
+    def close(self):
+        if self._handle:
+            _lib.lib().fb200_model_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- evaluation --------------------------------------------------------
+    def _flags(self, xp, yp, zp, reference_order):
+        big = max(self.max_coord, _max_abs(xp, yp, zp))
+        if reference_order or not (big <= FAST_PATH_MAX_COORD):
+            return _lib.REFERENCE_ORDER
+        return 0
+
+    def fields(self, xp, yp, zp, names, dens=None, pmag=None, fvec=None,
+               reference_order=False, scaled=True):
+        """
+        Evaluate several components in one pass.
+
+        Returns a dict ``{name: array}``.  ``dens`` (float) / ``pmag``
+        (3-vector) replace the per-prism property; ``fvec`` is required for
+        ``'tf'``.  ``scaled=False`` returns SI values without the unit factor.
+        """
+        xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
+        _check_points(xp, yp, zp, 'shape')
+        names = list(names)
+        ids = sorted(set(_lib.FIELD_ID[nm] for nm in names))
+        mask = 0
+        for i in ids:
+            mask |= 1 << i
+        n = xp.size
+        out = numpy.zeros((len(ids), n), dtype=numpy.float64)
+        if n and self.size:
+            scale = numpy.array([unit_scale(_lib.FIELDS[i]) if scaled else 1.0 for i in ids])
+            dens_arr = None if dens is None else numpy.array([dens], dtype=numpy.float64)
+            pmag_arr = None if pmag is None else numpy.ascontiguousarray(pmag, dtype=numpy.float64)
+            fvec_arr = None if fvec is None else numpy.ascontiguousarray(fvec, dtype=numpy.float64)
+            _lib.check(_lib.lib().fb200_forward(
+                self._handle, xp.ctypes.data, yp.ctypes.data, zp.ctypes.data, n, mask,
+                _lib.dptr(dens_arr), _lib.dptr(pmag_arr), _lib.dptr(fvec_arr),
+                _lib.dptr(scale), out.ctypes.data, n,
+                self._flags(xp, yp, zp, reference_order)))
+        return {_lib.FIELDS[i]: out[c] for c, i in enumerate(ids)}
+
+    def jacobian(self, xp, yp, zp, field='gz', pmag=None, fvec=None, transposed=False,
+                 reference_order=False, scaled=True, out=None):
+        """
+        Dense sensitivity matrix of ``field`` for unit physical property.
+
+        ``J[l, q]`` = effect at point l of prism q alone with density 1
+        (gravity) or magnetization ``pmag`` (magnetic): column q is what the
+        reference's ``prism.<field>(x, y, z, [cell_q], dens=1)`` returns
+        (eqlayer.py:108-111).  C-order ``(npoints, nprisms)`` float64, or
+        ``(nprisms, npoints)`` with ``transposed=True`` (imaging.py:116-117).
+        """
+        xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
+        _check_points(xp, yp, zp, 'shape')
+        fid = _lib.FIELD_ID[field]
+        n, m = xp.size, self.size
+        shape = (m, n) if transposed else (n, m)
+        if out is None:
+            out = numpy.zeros(shape, dtype=numpy.float64)
+        if out.shape != shape or out.dtype != numpy.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
+        if n and m:
+            if field in MAGNETIC_FIELDS:
+                if pmag is None:
+                    raise ValueError("magnetic Jacobians need the unit magnetization pmag")
+                unit = numpy.ascontiguousarray(pmag, dtype=numpy.float64)
+            else:
+                unit = numpy.array([1.0])
+            fvec_arr = None if fvec is None else numpy.ascontiguousarray(fvec, dtype=numpy.float64)
+            flags = self._flags(xp, yp, zp, reference_order)
+            if transposed:
+                flags |= _lib.TRANSPOSED
+            _lib.check(_lib.lib().fb200_jacobian(
+                self._handle, xp.ctypes.data, yp.ctypes.data, zp.ctypes.data, n, fid,
+                _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
+                out.ctypes.data, shape[1], flags))
+        return out
+
+    def last_kernel_ms(self):
+        """(device milliseconds, kernel launches) of the last evaluation."""
+        ms, launches = ctypes.c_double(0), ctypes.c_int(0)
+        _lib.check(_lib.lib().fb200_last_kernel_ms(self._handle, ctypes.byref(ms),
+                                                   ctypes.byref(launches)))
+        return ms.value, launches.value
+
+
+# --------------------------------------------------------------------------
+# one-shot helpers behind the drop-in functions
+# --------------------------------------------------------------------------
+def _gravity(names, xp, yp, zp, prisms, dens, what='length', scaled=True, **kw):
+    _check_points(xp, yp, zp, what)
+    with Model(prisms, 'density', keep_all=dens is not None, device=kw.pop('device', 0)) as model:
+        return model.fields(xp, yp, zp, names, dens=dens, scaled=scaled, **kw)
+
+
+def _pmag_vector(pmag, fvec):
+    # prism.py:641-645: a scalar pmag is an intensity along the inducing field
+    if pmag is None:
+        return None
+    if isinstance(pmag, (float, int)):
+        if fvec is None:
+            raise TypeError("pmag must be a 3-component vector")
+        return [pmag * fvec[0], pmag * fvec[1], pmag * fvec[2]]
+    mx, my, mz = pmag
+    return [mx, my, mz]
+
+
+def _magnetic(names, xp, yp, zp, prisms, pmag, fvec, what, **kw):
+    _check_points(xp, yp, zp, what)
+    pm = _pmag_vector(pmag, fvec)
+    with Model(prisms, 'magnetization', keep_all=pmag is not None, fvec=fvec,
+               device=kw.pop('device', 0)) as model:
+        return model.fields(xp, yp, zp, names, pmag=pm, fvec=fvec, **kw)
+
+
+def fields(xp, yp, zp, prisms, names, dens=None, pmag=None, inc=None, dec=None, **kw):
+    """
+    Several field components in ONE pass over the model (not in the reference).
+
+    * names : any of the fourteen field names; gravity and magnetic names may
+      be mixed (they run as two kernels)
+    * dens, pmag : property overrides as in the single-field functions
+    * inc, dec : inducing-field direction, needed for ``'tf'``
+
+    Returns a dict ``{name: array}`` in the reference's units.
+    """
+    names = list(names)
+    fvec = None if inc is None else utils.dircos(inc, dec)
+    res = {}
+    grav = [nm for nm in names if nm in GRAVITY_FIELDS]
+    magn = [nm for nm in names if nm in MAGNETIC_FIELDS]
+    unknown = [nm for nm in names if nm not in GRAVITY_FIELDS + MAGNETIC_FIELDS]
+    if unknown:
+        raise ValueError("unknown field(s) %s" % unknown)
+    if grav:
+        res.update(_gravity(grav, xp, yp, zp, prisms, dens, 'shape', **kw))
+    if magn:
+        if 'tf' in magn and fvec is None:
+            raise ValueError("'tf' needs the inducing field direction inc, dec")
+        res.update(_magnetic(magn, xp, yp, zp, prisms, pmag, fvec, 'shape', **kw))
+    return res
+
+
+def jacobian(xp, yp, zp, prisms, field='gz', inc=None, dec=None, pmag=None,
+             transposed=False, device=0, **kw):
+    """
+    Dense sensitivity (Jacobian) matrix of ``field`` with respect to the
+    physical property of every cell of ``prisms``.
+
+    Column ``q`` is the field of cell ``q`` alone with unit density (gravity),
+    or with magnetization ``pmag`` (magnetic fields; for ``'tf'`` pass the
+    inducing direction ``inc, dec``; ``pmag`` defaults to the unit vector along
+    it, the harvester convention, harvester.py:958-962).  Masked cells
+    (``None``) give zero columns, like the reference's per-cell loop
+    (eqlayer.py:108-111, imaging.py:116-117).  Shape ``(npoints, ncells)``, or
+    its transpose with ``transposed=True``.
+    """
+    _check_points(xp, yp, zp, 'shape')
+    fvec = None if inc is None else utils.dircos(inc, dec)
+    if field in MAGNETIC_FIELDS:
+        if field == 'tf' and fvec is None:
+            raise ValueError("'tf' needs the inducing field direction inc, dec")
+        if pmag is None:
+            if fvec is None:
+                raise ValueError("magnetic Jacobians need pmag or inc, dec")
+            pmag = fvec
+        pmag = _pmag_vector(pmag, fvec)
+    flat = flatten(prisms, None, override=True)
+    with Model(flat, None, device=device) as model:
+        jac = model.jacobian(xp, yp, zp, field, pmag=pmag, fvec=fvec,
+                             transposed=transposed, **kw)
+    if flat.size == flat.total:
+        return jac
+    # scatter the kept cells' columns back to mesh positions
+    if transposed:
+        full = numpy.zeros((flat.total, xp.size))
+        full[flat.index, :] = jac
+    else:
+        full = numpy.zeros((xp.size, flat.total))
+        full[:, flat.index] = jac
+    return full
+
+
+# --------------------------------------------------------------------------
+# the drop-in API: gravity
+# --------------------------------------------------------------------------
+def potential(xp, yp, zp, prisms, dens=None):
+    """
+    Calculates the gravitational potential (SI units!).
+
+    * xp, yp, zp : float64 arrays with the coordinates of the computation points
+    * prisms : list of ``Prism`` (``None`` entries and prisms without the
+      ``'density'`` property are ignored), a ``PrismMesh`` or a ``PrismRelief``
+    * dens : float or None; if given, used instead of every prism's density
+
+    Returns the field on xp, yp, zp.  Reference: prism.py:98-143.
+    """
+    return _gravity(['potential'], xp, yp, zp, prisms, dens)['potential']
+
+
+def gx(xp, yp, zp, prisms, dens=None):
+    """x (North) component of gravity in mGal.  Parameters as :func:`potential`.
+    Reference: prism.py:146-191."""
+    return _gravity(['gx'], xp, yp, zp, prisms, dens)['gx']
+
+
+def gy(xp, yp, zp, prisms, dens=None):
+    """y (East) component of gravity in mGal.  Parameters as :func:`potential`.
+    Reference: prism.py:194-239."""
+    return _gravity(['gy'], xp, yp, zp, prisms, dens)['gy']
+
+
+def gz(xp, yp, zp, prisms, dens=None):
+    """z (Down) component of gravity in mGal.  Parameters as :func:`potential`.
+    Reference: prism.py:242-287."""
+    return _gravity(['gz'], xp, yp, zp, prisms, dens)['gz']
+
+
+def gxx(xp, yp, zp, prisms, dens=None):
+    """xx component of the gravity gradient tensor in Eotvos.  Parameters as
+    :func:`potential`.  Reference: prism.py:290-335."""
+    return _gravity(['gxx'], xp, yp, zp, prisms, dens)['gxx']
+
+
+def gxy(xp, yp, zp, prisms, dens=None):
+    """xy component of the gravity gradient tensor in Eotvos (with the
+    reference's singularity shift).  Reference: prism.py:338-391."""
+    return _gravity(['gxy'], xp, yp, zp, prisms, dens)['gxy']
+
+
+def gxz(xp, yp, zp, prisms, dens=None):
+    """xz component of the gravity gradient tensor in Eotvos (with the
+    reference's singularity shift).  Reference: prism.py:394-447."""
+    return _gravity(['gxz'], xp, yp, zp, prisms, dens)['gxz']
+
+
+def gyy(xp, yp, zp, prisms, dens=None):
+    """yy component of the gravity gradient tensor in Eotvos.
+    Reference: prism.py:450-495."""
+    return _gravity(['gyy'], xp, yp, zp, prisms, dens)['gyy']
+
+
+def gyz(xp, yp, zp, prisms, dens=None):
+    """yz component of the gravity gradient tensor in Eotvos (with the
+    reference's singularity shift).  Reference: prism.py:498-551."""
+    return _gravity(['gyz'], xp, yp, zp, prisms, dens)['gyz']
+
+
+def gzz(xp, yp, zp, prisms, dens=None):
+    """zz component of the gravity gradient tensor in Eotvos.
+    Reference: prism.py:554-599."""
+    return _gravity(['gzz'], xp, yp, zp, prisms, dens)['gzz']
+
+
+# --------------------------------------------------------------------------
+# the drop-in API: magnetic
+# --------------------------------------------------------------------------
+def tf(xp, yp, zp, prisms, inc, dec, pmag=None):
+    """
+    Total-field magnetic anomaly in nT.
+
+    * prisms : prisms without the ``'magnetization'`` property are ignored; a
+      scalar magnetization is an intensity along the inducing field
+    * inc, dec : inclination and declination of the regional field (degrees)
+    * pmag : magnetization vector (or scalar intensity) used instead of the
+      prisms' own
+
+    Reference: prism.py:602-662.
+    """
+    fvec = utils.dircos(inc, dec)
+    return _magnetic(['tf'], xp, yp, zp, prisms, pmag, fvec, 'length')['tf']
+
+
+def bx(xp, yp, zp, prisms, pmag=None):
+    """x component of the magnetic induction in nT; ``'magnetization'`` must be
+    a vector.  Reference: prism.py:665-708."""
+    return _magnetic(['bx'], xp, yp, zp, prisms, pmag, None, 'shape')['bx']
+
+
+def by(xp, yp, zp, prisms, pmag=None):
+    """y component of the magnetic induction in nT; ``'magnetization'`` must be
+    a vector.  Reference: prism.py:711-754."""
+    return _magnetic(['by'], xp, yp, zp, prisms, pmag, None, 'shape')['by']
+
+
+def bz(xp, yp, zp, prisms, pmag=None):
+    """z component of the magnetic induction in nT; ``'magnetization'`` must be
+    a vector.  Reference: prism.py:757-800."""
+    return _magnetic(['bz'], xp, yp, zp, prisms, pmag, None, 'shape')['bz']
+
+
+# --------------------------------------------------------------------------
+# the drop-in API: second derivatives of the 1/r volume integral
+# --------------------------------------------------------------------------
+def _kernel(name, xp, yp, zp, prism):
+    # the reference calls _prism.g<comp> with density 1 and applies no unit
+    # factor (prism.py:828-835 ...), so xy/xz/yz inherit the singularity shift
+    return _gravity([name], xp, yp, zp, [prism], 1, 'shape', scaled=False)[name]
+
+
+def kernelxx(xp, yp, zp, prism):
+    """xx derivative of the 1/r volume integral of one prism.
+    Reference: prism.py:803-835."""
+    return _kernel('gxx', xp, yp, zp, prism)
+
+
+def kernelyy(xp, yp, zp, prism):
+    """yy derivative.  Reference: prism.py:838-870."""
+    return _kernel('gyy', xp, yp, zp, prism)
+
+
+def kernelzz(xp, yp, zp, prism):
+    """zz derivative.  Reference: prism.py:873-905."""
+    return _kernel('gzz', xp, yp, zp, prism)
+
+
+def kernelxy(xp, yp, zp, prism):
+    """xy derivative.  Reference: prism.py:908-940."""
+    return _kernel('gxy', xp, yp, zp, prism)
+
+
+def kernelxz(xp, yp, zp, prism):
+    """xz derivative.  Reference: prism.py:943-975."""
+    return _kernel('gxz', xp, yp, zp, prism)
+
+
+def kernelyz(xp, yp, zp, prism):
+    """yz derivative.  Reference: prism.py:978-1010."""
+    return _kernel('gyz', xp, yp, zp, prism)

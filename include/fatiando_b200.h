@@ -128,6 +128,8 @@ int fb200_jacobian(fb200_model *model,
  * prism's effect into caller-owned res[0..n) and never zeroes it
  * (_prism.pyx:72-479).  Host pointers.  Evaluated in reference order with
  * res[l] as the starting value of the running sum.                           */
+/* device used by the fb200_prism_* entry points below (default 0) */
+int fb200_set_default_device(int device);
 int fb200_prism_potential(const double *xp, const double *yp, const double *zp, int64_t n,
                           double x1, double x2, double y1, double y2, double z1, double z2,
                           double density, double *res);          /* _prism.pyx:454 */
@@ -184,6 +186,11 @@ int fb200_fp64_peak(int device, double seconds, double *burst_tflops,
                     double *sustained_tflops);
 /* Device-wide L2 flush: overwrite a buffer larger than L2 (bench hygiene).   */
 int fb200_flush_l2(int device);
+/* Evaluate one device math primitive over host arrays, so tests can pin the
+ * kernel's building blocks on the GPU: op 0 log(a/b), 1 atan(a/b) for b >= 0,
+ * 2 a/b, 3 branch-free sqrt(a), 4 library sqrt(a).                            */
+int fb200_debug_math(int device, int op, const double *a, const double *b,
+                     int64_t n, double *out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,336 @@
+"""
+Parity of the CUDA path with the oracle and the golden vectors (needs a GPU).
+
+Everything goes through the C ABI (ctypes -> libfatiando_b200.so).  Tolerance
+(helpers.py): |new - ref| <= 1e-9*|ref| + c*eps*A with A the sum of
+absolute terms from the instrumented oracle; c = 4 for the fused fast path,
+c = 0.25 for the reference-order path.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from helpers import (GRAV, MAG, KERN, C_FLOOR_FAST, C_FLOOR_EXACT, assert_parity, golden_model,
+                     prisms_from_golden)
+
+pytestmark = pytest.mark.gpu
+
+
+def _fvec(d):
+    from fatiando_b200 import utils
+    return utils.dircos(float(d['inc']), float(d['dec']))
+
+
+def _cond(oracle, f, d, fvec=None, scale=None):
+    bounds, props = golden_model(d, f, fvec)
+    return oracle.condition(f, d['xp'], d['yp'], d['zp'], bounds, props, scale=scale)
+
+
+@pytest.mark.parametrize("case", ["two_prisms", "c1_cookbook", "edge_cases", "skip_override"])
+def test_public_api_against_golden(gpu_lib, oracle, case):
+    """The drop-in functions on the reference's own test models."""
+    from fatiando_b200 import prism, mesher
+    d = load_golden(case)
+    model = prisms_from_golden(d, mesher.Prism)
+    fvec = _fvec(d) if 'inc' in d else None
+    xp, yp, zp = d['xp'], d['yp'], d['zp']
+    worst = 0.0
+    for f in GRAV + MAG:
+        if f not in d:
+            continue
+        if f == 'tf':
+            got = prism.tf(xp, yp, zp, model, float(d['inc']), float(d['dec']))
+        else:
+            got = getattr(prism, f)(xp, yp, zp, model)
+        worst = max(worst, assert_parity(got, d[f], _cond(oracle, f, d, fvec), C_FLOOR_FAST,
+                                         '%s/%s' % (case, f)))
+    assert worst > 0 or case == 'edge_cases'
+    if case == "two_prisms":
+        for c in KERN:
+            for q in (0, 1):
+                got = getattr(prism, 'kernel' + c)(xp, yp, zp, model[q])
+                b = tuple(d['bounds'][q:q + 1, k].copy() for k in range(6))
+                cond = oracle.condition('g' + c, xp, yp, zp, b, np.ones((1, 1)), scale=1.0)
+                assert_parity(got, d['kernel%s_%d' % (c, q)], cond, C_FLOOR_FAST, 'kernel' + c)
+
+
+def test_overrides_and_skipping(gpu_lib, oracle):
+    from fatiando_b200 import prism, mesher
+    d = load_golden("skip_override")
+    model = prisms_from_golden(d, mesher.Prism)
+    xp, yp, zp = d['xp'], d['yp'], d['zp']
+    keep = ~d['isnone']
+    b = tuple(np.ascontiguousarray(d['bounds'][keep][:, k]) for k in range(6))
+    m = int(keep.sum())
+    inc, dec = float(d['inc']), float(d['dec'])
+    fv = _fvec(d)
+    for f in GRAV:
+        cond = oracle.condition(f, xp, yp, zp, b, np.full((m, 1), -500.0))
+        assert_parity(getattr(prism, f)(xp, yp, zp, model, dens=-500), d[f + '_dens'], cond,
+                      C_FLOOR_FAST, f + ' dens=')
+    pm = d['pmag']
+    for f in ['bx', 'by', 'bz']:
+        cond = oracle.condition(f, xp, yp, zp, b, np.tile(pm, (m, 1)))
+        assert_parity(getattr(prism, f)(xp, yp, zp, model, pmag=pm), d[f + '_pmag'], cond,
+                      C_FLOOR_FAST, f + ' pmag=')
+    props = np.hstack([np.tile(pm, (m, 1)), np.tile(fv, (m, 1))])
+    cond = oracle.condition('tf', xp, yp, zp, b, props)
+    assert_parity(prism.tf(xp, yp, zp, model, inc, dec, pmag=pm), d['tf_pmag'], cond,
+                  C_FLOOR_FAST, 'tf pmag=')
+    props = np.hstack([np.tile(3.5 * np.array(fv), (m, 1)), np.tile(fv, (m, 1))])
+    cond = oracle.condition('tf', xp, yp, zp, b, props)
+    assert_parity(prism.tf(xp, yp, zp, model, inc, dec, pmag=3.5), d['tf_pmag_scalar'], cond,
+                  C_FLOOR_FAST, 'tf pmag scalar')
+    # empty and all-skipped models give zeros, like the reference
+    assert np.array_equal(prism.gz(xp, yp, zp, []), np.zeros_like(xp))
+    assert np.array_equal(prism.gz(xp, yp, zp, [None, model[2]]), np.zeros_like(xp))
+    d2 = load_golden("edge_cases")
+    sm = [mesher.Prism(-100, 100, -200, 200, 50, 300, {'magnetization': 2.0})]
+    cond = _cond(oracle, 'tf', d2, _fvec(d2))
+    assert_parity(prism.tf(d2['xp'], d2['yp'], d2['zp'], sm, float(d2['inc']), float(d2['dec'])),
+                  d2['tf_scalar_mag'], cond, C_FLOOR_FAST, 'scalar magnetization')
+    with pytest.raises(TypeError):
+        prism.bx(d2['xp'], d2['yp'], d2['zp'], sm)
+
+
+@pytest.mark.parametrize("case,names", [("prism_mesh", GRAV), ("mesh_magnetic", MAG),
+                                        ("prism_relief", ['gz', 'gzz', 'gxy', 'potential'])])
+def test_meshes_fused_and_reference_order(gpu_lib, oracle, case, names):
+    """Meshes flattened and evaluated in one fused pass, fast and reference-order."""
+    from fatiando_b200 import prism, mesher, utils
+    d = load_golden(case)
+    xp, yp, zp = d['xp'], d['yp'], d['zp']
+    fvec = _fvec(d) if 'inc' in d else None
+    if case == "prism_relief":
+        mesh = mesher.PrismRelief(float(d['relief_ref']), tuple(d['relief_dims']),
+                                  (d['relief_x'], d['relief_y'], d['relief_z']))
+        mesh.addprop('density', d['relief_density_in'])
+        prop = 'density'
+    else:
+        mesh = mesher.PrismMesh(tuple(d['mesh_bounds']), tuple(int(v) for v in d['mesh_shape']))
+        if case == "prism_mesh":
+            mesh.addprop('density', d['mesh_density'])
+            mesh.mask = [int(v) for v in d['mesh_mask']]
+            prop = 'density'
+        else:
+            mesh.addprop('magnetization', [r for r in d['mesh_magnetization']])
+            prop = 'magnetization'
+    with prism.Model(mesh, prop) as model:
+        fast = model.fields(xp, yp, zp, names, fvec=fvec)
+        exact = model.fields(xp, yp, zp, names, fvec=fvec, reference_order=True)
+    for f in names:
+        cond = _cond(oracle, f, d, fvec)
+        assert_parity(fast[f], d[f], cond, C_FLOOR_FAST, '%s/%s fast' % (case, f))
+        assert_parity(exact[f], d[f], cond, C_FLOOR_EXACT, '%s/%s exact' % (case, f))
+    # single-field calls equal the fused pass exactly (same kernel arithmetic per field)
+    one = getattr(prism, names[1])(xp, yp, zp, mesh) if names[1] != 'tf' else None
+    if one is not None:
+        assert_parity(one, d[names[1]], _cond(oracle, names[1], d, fvec), C_FLOOR_FAST)
+
+
+def test_cube_faces_symmetries_on_gpu(gpu_lib, oracle):
+    """test_prism.py:237-363 (test_around) through the new module, 21x21 faces."""
+    from fatiando_b200 import prism, mesher
+    d = load_golden("cube_faces")
+    model = prisms_from_golden(d, mesher.Prism)
+    b = tuple(d['bounds'][:, k].copy() for k in range(6))
+    props = d['density'][:, None].copy()
+    face = {}
+    for g in range(6):
+        x, y, z = d['xp_%d' % g], d['yp_%d' % g], d['zp_%d' % g]
+        res = prism.fields(x, y, z, model, GRAV)
+        for f in GRAV:
+            cond = oracle.condition(f, x, y, z, b, props)
+            assert_parity(res[f], d['%s_%d' % (f, g)], cond, C_FLOOR_FAST, '%s face %d' % (f, g))
+            face[f, g] = res[f]
+    aae = np.testing.assert_array_almost_equal
+    aae(face['gz', 0], -face['gz', 1], 10)
+    aae(face['gx', 2], -face['gx', 3], 10)
+    aae(face['gx', 2], -face['gz', 0], 10)
+    aae(face['gy', 4], -face['gz', 0], 10)
+    aae(face['gxx', 2], face['gzz', 0], 10)
+    aae(face['gyy', 4], face['gzz', 0], 10)
+    aae(face['gxy', 0], face['gxy', 1], 4)
+    aae(face['gxz', 0], -face['gxz', 1], 10)
+    aae(face['gyz', 2], face['gyz', 3], 4)
+    for g in range(6):
+        for a in range(g + 1, 6):
+            aae(face['potential', g], face['potential', a], 10)
+
+
+def test_reference_ffi_shape_accumulates(gpu_lib, oracle):
+    """`_prism.<field>(..., res)` adds one prism into res (14 entry points)."""
+    from fatiando_b200 import _prism
+    d = load_golden("two_prisms")
+    xp, yp, zp = d['xp'][::7].copy(), d['yp'][::7].copy(), d['zp'][::7].copy()
+    fv = _fvec(d)
+    for f in GRAV + MAG:
+        res = np.full(xp.size, 0.125)
+        ref = np.full(xp.size, 0.125)
+        for q in range(2):
+            bq = [float(v) for v in d['bounds'][q]]
+            if f == 'tf':
+                props = list(d['magnetization'][q]) + list(fv)
+            elif f in MAG:
+                props = list(d['magnetization'][q])
+            else:
+                props = [float(d['density'][q])]
+            getattr(_prism, f)(xp, yp, zp, *bq, *props, res)
+            oracle.accumulate(f, xp, yp, zp, *bq, props, ref)
+        bounds, pr = golden_model(d, f, fv)
+        cond = oracle.condition(f, xp, yp, zp, bounds, pr, scale=1.0) + 0.125
+        assert_parity(res, ref, cond, C_FLOOR_EXACT, '_prism.' + f)
+        assert not np.array_equal(res, np.full(xp.size, 0.125))
+
+
+def test_jacobian_against_reference_columns(gpu_lib, oracle):
+    from fatiando_b200 import prism, mesher
+    d = load_golden("jacobian")
+    mesh = mesher.PrismMesh(tuple(d['mesh_bounds']), tuple(int(v) for v in d['mesh_shape']))
+    xp, yp, zp = d['xp'], d['yp'], d['zp']
+    b = tuple(np.ascontiguousarray(d['bounds'][:, k]) for k in range(6))
+    m = b[0].size
+    for f in ['gz', 'gzz', 'gxy', 'potential']:
+        cond = np.empty((xp.size, m))
+        for q in range(m):
+            bq = tuple(a[q:q + 1] for a in b)
+            cond[:, q] = oracle.condition(f, xp, yp, zp, bq, np.ones((1, 1)))
+        jac = prism.jacobian(xp, yp, zp, mesh, f)
+        assert jac.shape == (xp.size, m) and jac.flags.c_contiguous
+        assert_parity(jac, d['jac_' + f], cond, C_FLOOR_FAST, 'jacobian ' + f)
+        jt = prism.jacobian(xp, yp, zp, mesh, f, transposed=True)
+        assert np.array_equal(jt, jac.T)
+        je = prism.jacobian(xp, yp, zp, mesh, f, reference_order=True)
+        assert_parity(je, d['jac_' + f], cond, C_FLOOR_EXACT, 'jacobian exact ' + f)
+    inc, dec = float(d['inc']), float(d['dec'])
+    fv = _fvec(d)
+    cond = np.empty((xp.size, m))
+    for q in range(m):
+        bq = tuple(a[q:q + 1] for a in b)
+        cond[:, q] = oracle.condition('tf', xp, yp, zp, bq,
+                                      np.array([list(d['jac_tf_pmag']) + list(fv)]))
+    jac = prism.jacobian(xp, yp, zp, mesh, 'tf', inc=inc, dec=dec)
+    assert_parity(jac, d['jac_tf'], cond, C_FLOOR_FAST, 'jacobian tf')
+    # masked cells give zero columns, like the reference's per-cell loop
+    mesh.mask = [1, 5]
+    jm = prism.jacobian(xp, yp, zp, mesh, 'gz')
+    assert np.array_equal(jm[:, [1, 5]], np.zeros((xp.size, 2)))
+    assert np.array_equal(np.delete(jm, [1, 5], axis=1),
+                          prism.jacobian(xp, yp, zp, mesh_cells(mesh), 'gz'))
+    # J @ density reproduces the forward field (linearity)
+    mesh.mask = []
+    dens = np.linspace(-500, 800, m)
+    mesh.addprop('density', dens)
+    gz = prism.gz(xp, yp, zp, mesh)
+    np.testing.assert_allclose(prism.jacobian(xp, yp, zp, mesh, 'gz') @ dens, gz, rtol=1e-9,
+                               atol=1e-12 * np.abs(gz).max())
+
+
+def mesh_cells(mesh):
+    return [c for c in mesh if c is not None]
+
+
+def test_random_models_all_component_sets(gpu_lib, oracle):
+    """Seeded random models/points incl. points on faces, edges and vertices."""
+    from fatiando_b200 import prism
+    from fatiando_b200.flatten import FlatModel
+    rs = np.random.RandomState(11)
+    n, m = 700, 33
+    xp, yp, zp = rs.uniform(-5e3, 5e3, n), rs.uniform(-5e3, 5e3, n), rs.uniform(-800, 1200, n)
+    x1 = rs.uniform(-4e3, 3e3, m); x2 = x1 + rs.uniform(10, 1500, m)
+    y1 = rs.uniform(-4e3, 3e3, m); y2 = y1 + rs.uniform(10, 1500, m)
+    z1 = rs.uniform(0, 1e3, m); z2 = z1 + rs.uniform(10, 1500, m)
+    xp[:m], yp[:m], zp[:m] = x1, y1, z2 + 100
+    xp[m:2 * m], yp[m:2 * m], zp[m:2 * m] = x2, y1 - 50, z1
+    xp[2 * m:3 * m], yp[2 * m:3 * m], zp[2 * m:3 * m] = x1 - 30, y2, z2
+    xp[3 * m:4 * m], yp[3 * m:4 * m], zp[3 * m:4 * m] = x1, y2, z1            # vertices
+    xp[4 * m:5 * m], yp[4 * m:5 * m], zp[4 * m:5 * m] = 0.5 * (x1 + x2), 0.5 * (y1 + y2), 0.5 * (z1 + z2)
+    b = (x1, x2, y1, y2, z1, z2)
+    dens = rs.uniform(-1e3, 1e3, m)
+    mag = rs.uniform(-2, 2, (m, 3))
+    fv = [0.3, 0.5, 0.81]
+    flat_g = FlatModel(list(b), dens, None, np.arange(m), m)
+    flat_m = FlatModel(list(b), None, mag, np.arange(m), m)
+    sets = [['gz'], ['gx', 'gy', 'gz'], GRAV[4:], ['gz'] + GRAV[4:], GRAV[1:], GRAV,
+            ['gx', 'gxy', 'gzz'], ['potential', 'gyz']]
+    with prism.Model(flat_g, 'density') as model:
+        for names in sets:
+            res = model.fields(xp, yp, zp, names)
+            for f in names:
+                ref = oracle.model(f, xp, yp, zp, b, dens[:, None])
+                cond = oracle.condition(f, xp, yp, zp, b, dens[:, None])
+                assert_parity(res[f], ref, cond, C_FLOOR_FAST, 'random %s in %s' % (f, names))
+    with prism.Model(flat_m, 'magnetization') as model:
+        for names in [['tf'], ['bx'], ['by'], ['bz'], ['bx', 'by', 'bz'], MAG, ['tf', 'bz']]:
+            res = model.fields(xp, yp, zp, names, fvec=fv)
+            for f in names:
+                props = mag if f != 'tf' else np.hstack([mag, np.tile(fv, (m, 1))])
+                ref = oracle.model(f, xp, yp, zp, b, props)
+                cond = oracle.condition(f, xp, yp, zp, b, props)
+                assert_parity(res[f], ref, cond, C_FLOOR_FAST, 'random %s in %s' % (f, names))
+
+
+def test_prism_split_and_many_tiles(gpu_lib, oracle):
+    """Few points x many prisms: the prism-split path and ragged tile tails."""
+    from fatiando_b200 import prism, mesher
+    rs = np.random.RandomState(5)
+    mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (7, 23, 31))     # 4991 cells
+    mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+    mesh.mask = list(range(0, mesh.size, 97))
+    xp, yp, zp = rs.uniform(0, 5000, 37), rs.uniform(0, 5000, 37), np.full(37, -150.0)
+    from fatiando_b200.flatten import flatten
+    flat = flatten(mesh, 'density')
+    b = tuple(flat.bounds)
+    names = ['gz', 'gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz']
+    res = prism.fields(xp, yp, zp, mesh, names)
+    for f in names:
+        ref = oracle.model(f, xp, yp, zp, b, flat.density[:, None], threads=8)
+        cond = oracle.condition(f, xp, yp, zp, b, flat.density[:, None], threads=8)
+        assert_parity(res[f], ref, cond, C_FLOOR_FAST, 'split ' + f)
+    again = prism.fields(xp, yp, zp, mesh, names)
+    for f in names:
+        assert np.array_equal(res[f], again[f])        # fixed-order reduction: reproducible
+
+
+def test_size_independent_properties_at_scale(gpu_lib):
+    """Config-sized run (C2: 50x50x20 mesh, 200x200 grid): properties, not an oracle."""
+    from fatiando_b200 import prism, mesher, gridder
+    rs = np.random.RandomState(0)
+    mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (20, 50, 50))
+    dens = rs.uniform(-1000, 1000, mesh.size)
+    mesh.addprop('density', dens)
+    xp, yp, zp = gridder.regular((0, 5000, 0, 5000), (200, 200), z=-150)
+    names = ['gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz']
+    with prism.Model(mesh, 'density') as model:
+        t = model.fields(xp, yp, zp, names)
+        lap = t['gxx'] + t['gyy'] + t['gzz']
+        scale = np.abs(t['gzz']).max()
+        assert np.max(np.abs(lap)) < 1e-9 * scale        # Laplace outside the sources
+        # observation split invariance: any sub-block equals the same rows of the full run
+        sl = slice(12345, 23456)
+        part = model.fields(xp[sl].copy(), yp[sl].copy(), zp[sl].copy(), names)
+        for f in names:
+            assert np.array_equal(part[f], t[f][sl])
+    # linearity in the property
+    mesh.addprop('density', 2.0 * dens)
+    t2 = prism.gzz(xp, yp, zp, mesh)
+    np.testing.assert_allclose(t2, 2.0 * t['gzz'], rtol=1e-12, atol=1e-12 * scale)
+
+
+def test_input_contract(gpu_lib):
+    from fatiando_b200 import prism, mesher
+    model = [mesher.Prism(0, 1, 0, 1, 0, 1, {'density': 1.0})]
+    x = np.zeros(4)
+    with pytest.raises(ValueError):
+        prism.gz(x.astype(np.float32), x.astype(np.float32), x.astype(np.float32), model)
+    with pytest.raises(ValueError):
+        prism.gz(x.reshape(2, 2), x.reshape(2, 2), x.reshape(2, 2), model)
+    with pytest.raises(AttributeError):
+        prism.gz([0.0], [0.0], [0.0], model)
+    big = np.arange(8.0)
+    got = prism.gz(big[::2], big[::2], -big[::2] - 1, model)      # strided views accepted
+    want = prism.gz(big[::2].copy(), big[::2].copy(), (-big[::2] - 1).copy(), model)
+    assert np.array_equal(got, want)
+    assert prism.gz(np.zeros(0), np.zeros(0), np.zeros(0), model).shape == (0,)
+    nan = prism.gz(np.array([np.nan]), np.array([0.0]), np.array([-1.0]), model)
+    assert np.isnan(nan[0])
