@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfatiando_b200.so")
 
 OK, EINVAL, ECUDA, EPROP, EUNSUP = 0, -1, -2, -3, -4
-DEVICE_POINTERS, REFERENCE_ORDER, TRANSPOSED = 1, 2, 4
+DEVICE_POINTERS, REFERENCE_ORDER, TRANSPOSED, NO_PRISM_SPLIT = 1, 2, 4, 8
 
 FIELDS = ("potential", "gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz",
           "gzz", "tf", "bx", "by", "bz")

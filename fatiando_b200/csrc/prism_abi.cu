@@ -396,7 +396,7 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         return fail(FB200_EINVAL, "invalid field mask");
     if (n > 0 && (!xp || !yp || !zp || !out)) return fail(FB200_EINVAL, "NULL point or output array");
     if (ld_out < n) return fail(FB200_EINVAL, "ld_out smaller than n");
-    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER))
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_NO_PRISM_SPLIT))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_forward");
     const uint32_t gmask = field_mask & GRAVITY_MASK, mmask = field_mask & MAGNETIC_MASK;
     if (gmask && !mod->d_dens && !dens_override)
@@ -407,6 +407,7 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
+    const bool split = !exact && !(flags & FB200_NO_PRISM_SPLIT);
     const int nreq = popc(field_mask);
     if (n == 0) return FB200_OK;
 
@@ -447,14 +448,14 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         CK(cudaEventRecord(mod->ev0, mod->stream));
         if (gmask) {
             for (uint32_t set : cover(gmask, kGravitySets)) {
-                int rc = run_set(mod, set, field_mask, exact, !exact, d_xp, d_yp, d_zp, n,
+                int rc = run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
                                  dens_override, fvec, scale, d_init, d_out, ld);
                 if (rc != FB200_OK) return rc;
             }
         }
         if (mmask) {
             for (uint32_t set : cover(mmask, kMagneticSets)) {
-                int rc = run_set(mod, set, field_mask, exact, !exact, d_xp, d_yp, d_zp, n,
+                int rc = run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
                                  pmag_override, fvec, scale, d_init, d_out, ld);
                 if (rc != FB200_OK) return rc;
             }

@@ -50,27 +50,55 @@ template <int OWN, LogMode MODE>
 struct LogFam {
     double v[4];
 
+    // log( prod nf / prod df ) with the reference's safe_log(0) = 0 rule
+    // (_prism.pyx:28-34): a factor that is exactly zero drops out.  Zero
+    // factors are detected on the PRODUCTS (two compares per group); they occur
+    // when the point lies on the extension of an edge -- exactly, or so nearly
+    // that sqrt() rounds r to |d| -- and take the short fix-up below.
+    template <int K>
+    static FB_HD_M double group(const double (&nf)[K], const double (&df)[K])
+    {
+        double num = nf[0], den = df[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) { num *= nf[k]; den *= df[k]; }
+        if (num == 0.0 || den == 0.0) {
+            num = 1.0; den = 1.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                num *= (nf[k] == 0.0) ? 1.0 : nf[k];
+                den *= (df[k] == 0.0) ? 1.0 : df[k];
+            }
+        }
+        return fm::log_ratio(num, den);
+    }
+
     FB_HD_M void eval(const double (&a)[8])
     {
-        using namespace fm;
 #define A_(o, p, q) a[cidx<OWN>(o, p, q)]
         if constexpr (MODE == LM_FULL) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int p = 0; p < 2; ++p)
-                    v[q * 2 + p] = log_ratio(A_(0, p, q), A_(1, p, q));
+                for (int p = 0; p < 2; ++p) {
+                    const double nf[1] = {A_(0, p, q)}, df[1] = {A_(1, p, q)};
+                    v[q * 2 + p] = group(nf, df);
+                }
         } else if constexpr (MODE == LM_BYQ) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-                v[q] = log_ratio(A_(0, 0, q) * A_(1, 1, q), A_(1, 0, q) * A_(0, 1, q));
+            for (int q = 0; q < 2; ++q) {
+                const double nf[2] = {A_(0, 0, q), A_(1, 1, q)}, df[2] = {A_(1, 0, q), A_(0, 1, q)};
+                v[q] = group(nf, df);
+            }
         } else if constexpr (MODE == LM_BYP) {
 #pragma unroll
-            for (int p = 0; p < 2; ++p)
-                v[p] = log_ratio(A_(0, p, 0) * A_(1, p, 1), A_(1, p, 0) * A_(0, p, 1));
+            for (int p = 0; p < 2; ++p) {
+                const double nf[2] = {A_(0, p, 0), A_(1, p, 1)}, df[2] = {A_(1, p, 0), A_(0, p, 1)};
+                v[p] = group(nf, df);
+            }
         } else if constexpr (MODE == LM_ALL) {
-            v[0] = log_ratio((A_(0, 0, 0) * A_(1, 1, 0)) * (A_(1, 0, 1) * A_(0, 1, 1)),
-                             (A_(1, 0, 0) * A_(0, 1, 0)) * (A_(0, 0, 1) * A_(1, 1, 1)));
+            const double nf[4] = {A_(0, 0, 0), A_(1, 1, 0), A_(1, 0, 1), A_(0, 1, 1)};
+            const double df[4] = {A_(1, 0, 0), A_(0, 1, 0), A_(0, 0, 1), A_(1, 1, 1)};
+            v[0] = group(nf, df);
         }
 #undef A_
     }
@@ -270,10 +298,6 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
         for (int c = 0; c < 8; ++c) {
             const int i = c & 1, j = (c >> 1) & 1, k = c >> 2;
             const bool neg = (i + j + k) & 1;
-            // safe_log(0) = 0: the factor drops out of the product
-            if constexpr (MLX != LM_NONE) if (zy[j] & zz[k] & (X[i] <= 0.0)) ax[c] = 1.0;
-            if constexpr (MLY != LM_NONE) if (zx[i] & zz[k] & (Y[j] <= 0.0)) ay[c] = 1.0;
-            if constexpr (MLZ != LM_NONE) if (zx[i] & zy[j] & (Z[k] <= 0.0)) az[c] = 1.0;
             // safe_atan2(0, 0) = 0: unit factor
             if constexpr (MAX_ != AM_NONE) if (zx[i] & (zy[j] | zz[k])) rex[c] = 1.0;
             if constexpr (MAY_ != AM_NONE) if (zy[j] & (zx[i] | zz[k])) rey[c] = 1.0;

@@ -146,13 +146,16 @@ class Model(object):
         return 0
 
     def fields(self, xp, yp, zp, names, dens=None, pmag=None, fvec=None,
-               reference_order=False, scaled=True):
+               reference_order=False, scaled=True, list_order=False):
         """
         Evaluate several components in one pass.
 
         Returns a dict ``{name: array}``.  ``dens`` (float) / ``pmag``
         (3-vector) replace the per-prism property; ``fvec`` is required for
         ``'tf'``.  ``scaled=False`` returns SI values without the unit factor.
+        ``list_order=True`` forbids splitting the prism list over thread blocks:
+        every point then sums the prisms strictly in list order, so any
+        observation shard of a run reproduces the same bits as the full run.
         """
         xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
         _check_points(xp, yp, zp, 'shape')
@@ -172,7 +175,8 @@ class Model(object):
                 self._handle, xp.ctypes.data, yp.ctypes.data, zp.ctypes.data, n, mask,
                 _lib.dptr(dens_arr), _lib.dptr(pmag_arr), _lib.dptr(fvec_arr),
                 _lib.dptr(scale), out.ctypes.data, n,
-                self._flags(xp, yp, zp, reference_order)))
+                self._flags(xp, yp, zp, reference_order)
+                | (_lib.NO_PRISM_SPLIT if list_order else 0)))
         return {_lib.FIELDS[i]: out[c] for c, i in enumerate(ids)}
 
     def jacobian(self, xp, yp, zp, field='gz', pmag=None, fvec=None, transposed=False,

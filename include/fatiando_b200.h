@@ -56,6 +56,11 @@ enum fb200_field {
 /* jacobian only: write the transpose, out[cell * ld + point]
  * (the layout imaging.py:116-117 builds)                                    */
 #define FB200_TRANSPOSED       (1u << 2)
+/* forward only: never split the prism list over thread blocks, so that every
+ * point sums the prisms strictly in list order whatever the number of points
+ * (results are then bit-identical between a full run and any observation
+ * shard of it; small problems lose occupancy)                               */
+#define FB200_NO_PRISM_SPLIT   (1u << 3)
 
 typedef struct fb200_model fb200_model;
 

@@ -1,0 +1,161 @@
+"""
+Numerics of the fused fast path, studied on the HOST (no GPU needed).
+
+tests/hostsim compiles the device math headers (prism_fast.cuh, prism_exact.cuh)
+with g++; this file compares them with the oracle under the project's stated
+tolerance.  It validates the ALGEBRA of the collapsed corner sums and the custom
+log/atan/sqrt; the same comparisons run on the real kernels in test_gpu_parity.py.
+hostsim is test infrastructure: the product never loads it.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from helpers import C_FLOOR_FAST, EPS, assert_parity, golden_model
+
+HS_DIR = os.path.join(ROOT, "tests", "hostsim")
+dp = ctypes.POINTER(ctypes.c_double)
+SETS_G = [0x001, 0x002, 0x004, 0x008, 0x010, 0x020, 0x040, 0x080, 0x100, 0x200, 0x00E, 0x3F0,
+          0x3F8, 0x3FE, 0x3FF]
+SETS_M = [0x0400, 0x0800, 0x1000, 0x2000, 0x3800, 0x3C00]
+NAMES = ("potential", "gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz", "gzz",
+         "tf", "bx", "by", "bz")
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    subprocess.check_call(["make", "-s", "-C", HS_DIR])
+    return ctypes.CDLL(os.path.join(HS_DIR, "libhostsim.so"))
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def forward(H, mask, exact, xp, yp, zp, b, props, f=(0, 0, 0)):
+    xp, yp, zp = (np.ascontiguousarray(a, dtype=float) for a in (xp, yp, zp))
+    b = [np.ascontiguousarray(a, dtype=float) for a in b]
+    n, m = xp.size, b[0].size
+    out = np.zeros((bin(mask).count('1'), n))
+    cols = [np.ascontiguousarray(props[:, i]) for i in range(props.shape[1])]
+    barr = (dp * 6)(*[_p(a) for a in b])
+    parr = (dp * 3)(*([_p(a) for a in cols] + [None] * (3 - len(cols))))
+    fv = np.array(f, dtype=float)
+    rc = H.hostsim_forward(ctypes.c_uint32(mask), int(exact), _p(xp), _p(yp), _p(zp),
+                           ctypes.c_size_t(n), ctypes.c_size_t(m), barr, parr, _p(fv), _p(out))
+    assert rc == 0
+    return out
+
+
+def check_sets(H, oracle, sets, xp, yp, zp, b, props, f=(0, 0, 0), what=''):
+    worst = 0.0
+    cache = {}
+    for mask in sets:
+        fast = forward(H, mask, 0, xp, yp, zp, b, props, f)
+        exact = forward(H, mask, 1, xp, yp, zp, b, props, f)
+        fields = [NAMES[i] for i in range(14) if mask >> i & 1]
+        for c, fld in enumerate(fields):
+            if fld not in cache:
+                pr = props if fld != 'tf' else np.hstack([props, np.tile(f, (props.shape[0], 1))])
+                cache[fld] = (oracle.model(fld, xp, yp, zp, b, pr, scale=1.0),
+                              oracle.condition(fld, xp, yp, zp, b, pr, scale=1.0))
+            ref, cond = cache[fld]
+            # host build of the reference-order evaluator: same libm, same order -> same bits
+            assert np.array_equal(exact[c], ref), '%s %s exact' % (what, fld)
+            worst = max(worst, assert_parity(fast[c], ref, cond, C_FLOOR_FAST,
+                                             '%s %s in set 0x%x' % (what, fld, mask)))
+    return worst
+
+
+def test_primitives_against_mpmath(hostsim):
+    import mpmath as mp
+    mp.mp.dps = 40
+    rs = np.random.RandomState(0)
+    n = 8000
+
+    def run(name, a, b):
+        a, b = np.ascontiguousarray(a, float), np.ascontiguousarray(b, float)
+        out = np.empty_like(a)
+        getattr(hostsim, name)(_p(a), _p(b), ctypes.c_size_t(a.size), _p(out))
+        return out
+    a = rs.uniform(-1, 1, n) * 10.0 ** rs.uniform(-20, 20, n)
+    b = rs.uniform(0.5, 1, n) * 10.0 ** rs.uniform(-30, 40, n)
+    assert np.max(np.abs(run('hostsim_div', a, b) - a / b) / np.spacing(np.abs(a / b))) <= 1.0
+    num = rs.uniform(1, 2, n) * 10.0 ** rs.uniform(-10, 30, n)
+    den = np.abs(num * np.concatenate([1 + rs.uniform(-1, 1, n // 2) * 10.0 ** rs.uniform(-12, 0, n // 2),
+                                       10.0 ** rs.uniform(-16, 16, n // 2)])) + 1e-300
+    ex = np.array([float(mp.log(mp.mpf(x) / mp.mpf(y))) for x, y in zip(num, den)])
+    assert np.max(np.abs(run('hostsim_log_ratio', num, den) - ex) / np.spacing(np.abs(ex))) <= 2.0
+    re = np.abs(rs.normal(size=n)) * 10.0 ** rs.uniform(-5, 20, n)
+    im = rs.normal(size=n) * 10.0 ** rs.uniform(-5, 20, n)
+    re[:50] = 0.0
+    ex = np.array([float(mp.atan2(mp.mpf(y), mp.mpf(x))) for x, y in zip(re, im)])
+    assert np.max(np.abs(run('hostsim_atan_rhp', im, re) - ex) / np.spacing(np.abs(ex))) <= 2.0
+
+
+def test_near_field_random_model(hostsim, oracle):
+    rs = np.random.RandomState(0)
+    n, m = 600, 25
+    xp, yp, zp = rs.uniform(-5e3, 5e3, n), rs.uniform(-5e3, 5e3, n), rs.uniform(-500, 1500, n)
+    x1 = rs.uniform(-4e3, 3e3, m); x2 = x1 + rs.uniform(10, 1500, m)
+    y1 = rs.uniform(-4e3, 3e3, m); y2 = y1 + rs.uniform(10, 1500, m)
+    z1 = rs.uniform(0, 1e3, m); z2 = z1 + rs.uniform(10, 1500, m)
+    b = (x1, x2, y1, y2, z1, z2)
+    w = check_sets(hostsim, oracle, SETS_G, xp, yp, zp, b, rs.uniform(-1e3, 1e3, (m, 1)), what='near')
+    assert w <= 1.0
+    check_sets(hostsim, oracle, SETS_M, xp, yp, zp, b, rs.uniform(-2, 2, (m, 3)), (0.3, 0.5, 0.81), 'near')
+
+
+def test_points_on_and_almost_on_faces_edges_vertices(hostsim, oracle):
+    """Exact zeros (aligned grids) and near-zeros where sqrt() absorbs the offset."""
+    rs = np.random.RandomState(4)
+    xe = np.linspace(0, 600, 7)
+    I, J, K = np.meshgrid(range(6), range(6), range(3), indexing='ij')
+    b = [xe[I.ravel()], xe[I.ravel() + 1], xe[J.ravel()], xe[J.ravel() + 1],
+         100.0 * K.ravel(), 100.0 * K.ravel() + 100.0]
+    m = b[0].size
+    g = np.linspace(-100, 700, 9)
+    PX, PY, PZ = np.meshgrid(g, g, np.array([-100., 0., 100., 150., 300., 400.]), indexing='ij')
+    xp, yp, zp = PX.ravel().copy(), PY.ravel().copy(), PZ.ravel().copy()
+    # nudge a third of the points by relative 1e-16 .. 1e-7: almost aligned
+    sel = rs.rand(xp.size) < 0.33
+    xp[sel] += xp[sel] * 10.0 ** rs.uniform(-16, -7, sel.sum())
+    sel = rs.rand(xp.size) < 0.33
+    yp[sel] -= (yp[sel] + 1.0) * 10.0 ** rs.uniform(-16, -7, sel.sum())
+    sel = rs.rand(xp.size) < 0.2
+    zp[sel] += (zp[sel] + 1.0) * 10.0 ** rs.uniform(-16, -7, sel.sum())
+    check_sets(hostsim, oracle, [0x3FF, 0x008, 0x3F0, 0x020, 0x100, 0x040], xp, yp, zp, b,
+               rs.uniform(-1e3, 1e3, (m, 1)), what='aligned')
+    check_sets(hostsim, oracle, [0x3C00, 0x0400, 0x0800], xp, yp, zp, b, rs.uniform(-2, 2, (m, 3)),
+               (0.3, 0.5, 0.81), 'aligned')
+    d = load_golden("edge_cases")
+    bounds, props = golden_model(d, 'gz')
+    check_sets(hostsim, oracle, SETS_G, d['xp'], d['yp'], d['zp'], bounds, props, what='edge')
+
+
+def test_far_field_relief(hostsim, oracle):
+    rs = np.random.RandomState(3)
+    xs = np.linspace(0, 1e6, 40)
+    X, Y = np.meshgrid(xs, xs, indexing='ij')
+    xc, yc = X.ravel(), Y.ravel()
+    dx = xs[1] - xs[0]
+    h = 3000 * np.exp(-((xc - 4e5) ** 2 + (yc - 6e5) ** 2) / 2e5 ** 2) + rs.uniform(0, 200, xc.size) - 500
+    zc = -h
+    b = (xc - 0.5 * dx, xc + 0.5 * dx, yc - 0.5 * dx, yc + 0.5 * dx,
+         np.where(zc <= 0, zc, 0.0), np.where(zc <= 0, 0.0, zc))
+    dens = np.where(zc > 0, -2670.0, 2670.0)[:, None]
+    g = np.linspace(0, 1e6, 12)
+    PX, PY = np.meshgrid(g, g, indexing='ij')
+    xp, yp = PX.ravel().copy(), PY.ravel().copy()
+    zp = np.full(xp.size, -5000.0)
+    w = check_sets(hostsim, oracle, [0x008, 0x3F8], xp, yp, zp, b, dens, what='relief')
+    assert w <= 1.0
+    # how tight it really is: the far-field discrepancy is a small fraction of eps*A
+    fast = forward(hostsim, 0x008, 0, xp, yp, zp, b, dens)[0]
+    ref = oracle.model('gz', xp, yp, zp, b, dens, scale=1.0)
+    cond = oracle.condition('gz', xp, yp, zp, b, dens, scale=1.0)
+    assert np.max(np.abs(fast - ref) / (EPS * cond)) < 0.25

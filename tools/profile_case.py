@@ -1,0 +1,47 @@
+"""
+Run one benchmark workload a few times through the C ABI (host buffers), for ncu.
+
+    python tools/profile_case.py c2 [reps] [--exact]
+
+Same workloads as bench.py; no torch import, so ncu replays stay short.
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import bench         # noqa: E402
+from fatiando_b200 import prism   # noqa: E402
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 3
+    exact = "--exact" in sys.argv
+    w = bench.make_workload(name, 1)
+    if "--points" in sys.argv:
+        k = int(sys.argv[sys.argv.index("--points") + 1])
+        for key in ("xp", "yp", "zp"):
+            w[key] = np.ascontiguousarray(w[key][:k])
+    with prism.Model(w['model'], w['prop'], keep_all=w['prop'] is None, fvec=w['fvec']) as model:
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            if w['kind'] == 'jacobian':
+                rows = min(w['xp'].size, 2048)
+                model.jacobian(w['xp'][:rows], w['yp'][:rows], w['zp'][:rows], w['names'][0],
+                               reference_order=exact)
+                pairs = rows * model.size
+            else:
+                model.fields(w['xp'], w['yp'], w['zp'], w['names'], fvec=w['fvec'],
+                             reference_order=exact)
+                pairs = w['xp'].size * model.size
+            ms, nl = model.last_kernel_ms()
+            print("%s: %d pairs, kernels %.3f ms (%d launches) -> %.3e pairs/s; call %.1f ms" % (
+                name, pairs, ms, nl, pairs / (ms * 1e-3), 1e3 * (time.perf_counter() - t0)))
+
+
+if __name__ == "__main__":
+    main()
