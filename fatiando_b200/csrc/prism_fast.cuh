@@ -11,10 +11,15 @@
 //   * the 1e-5*size shift of r for gxy/gxz/gyz when the point is aligned with
 //     an edge on the far side (:327-330, :359-362, :418-421) -- and NOT for
 //     tf/bx/by/bz, which use the unshifted kernels (:94-99).
-// They only matter when a coordinate difference is exactly zero; those pairs
-// take a short predicated fix-up block.  Differences so small that their
-// squares underflow (|d| < 2^-480, never seen in metres) fall back to the
-// reference-order evaluator for that pair.
+// They only matter when a coordinate difference is exactly zero or a log
+// argument rounds to exactly zero (point on, or within ~1e-8 relative of, the
+// extension of an edge).  The hot path carries none of that: it detects those
+// pairs with a handful of ALU-pipe tests and two compares per log group, and
+// if ANY lane of the warp has one (warp vote, so the warp never diverges) the
+// whole warp re-evaluates the pair with the out-of-line "careful" variant,
+// which applies the special cases with selects.  Differences so small that
+// their squares underflow (|d| < 2^-480, never seen in metres) fall back to
+// the reference-order evaluator for that pair.
 #pragma once
 #include "prism_common.cuh"
 #include "prism_fastmath.cuh"
@@ -33,6 +38,7 @@ constexpr AtanMode atan_mode(bool byown, bool all)
 {
     return byown ? AM_BYOWN : all ? AM_ALL : AM_NONE;
 }
+constexpr int log_groups(LogMode m) { return m == LM_FULL ? 4 : (m == LM_BYQ || m == LM_BYP) ? 2 : m == LM_ALL ? 1 : 0; }
 
 // corner index c = k*4 + j*2 + i.  A family has an "own" axis o (the coordinate
 // that appears inside its log / as its atan denominator) and the two other
@@ -45,62 +51,67 @@ FB_HD constexpr int cidx(int o, int p, int q)
                     : ((q << 2) | (p << 1) | o);
 }
 
-// sum over the own axis (and more) of s*log(a), by groups
+// sum over the own axis (and more) of s*log(a), by groups.  Two steps so that
+// the caller can look at the products before any logarithm is taken:
+//   products(a): num[g], den[g] of each group, factors multiplied in a fixed order
+//   finish():    v[g] = log(num[g] / den[g])
 template <int OWN, LogMode MODE>
 struct LogFam {
-    double v[4];
+    static constexpr int NG = log_groups(MODE);
+    double num[NG > 0 ? NG : 1], den[NG > 0 ? NG : 1];
+    double v[NG > 0 ? NG : 1];
 
-    // log( prod nf / prod df ) with the reference's safe_log(0) = 0 rule
-    // (_prism.pyx:28-34): a factor that is exactly zero drops out.  Zero
-    // factors are detected on the PRODUCTS (two compares per group); they occur
-    // when the point lies on the extension of an edge -- exactly, or so nearly
-    // that sqrt() rounds r to |d| -- and take the short fix-up below.
-    template <int K>
-    static FB_HD_M double group(const double (&nf)[K], const double (&df)[K])
+    // CAREFUL: a factor that is exactly zero drops out -- the reference's
+    // safe_log(0) = 0 (_prism.pyx:28-34)
+    template <bool CAREFUL>
+    static FB_HD_M double fac(double a)
     {
-        double num = nf[0], den = df[0];
-#pragma unroll
-        for (int k = 1; k < K; ++k) { num *= nf[k]; den *= df[k]; }
-        if (num == 0.0 || den == 0.0) {
-            num = 1.0; den = 1.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                num *= (nf[k] == 0.0) ? 1.0 : nf[k];
-                den *= (df[k] == 0.0) ? 1.0 : df[k];
-            }
-        }
-        return fm::log_ratio(num, den);
+        if constexpr (CAREFUL) return (a == 0.0) ? 1.0 : a;
+        else return a;
     }
 
-    FB_HD_M void eval(const double (&a)[8])
+    template <bool CAREFUL>
+    FB_HD_M void products(const double (&a)[8])
     {
-#define A_(o, p, q) a[cidx<OWN>(o, p, q)]
+#define A_(o, p, q) fac<CAREFUL>(a[cidx<OWN>(o, p, q)])
         if constexpr (MODE == LM_FULL) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
-                    const double nf[1] = {A_(0, p, q)}, df[1] = {A_(1, p, q)};
-                    v[q * 2 + p] = group(nf, df);
+                    num[q * 2 + p] = A_(0, p, q);
+                    den[q * 2 + p] = A_(1, p, q);
                 }
         } else if constexpr (MODE == LM_BYQ) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const double nf[2] = {A_(0, 0, q), A_(1, 1, q)}, df[2] = {A_(1, 0, q), A_(0, 1, q)};
-                v[q] = group(nf, df);
+                num[q] = A_(0, 0, q) * A_(1, 1, q);
+                den[q] = A_(1, 0, q) * A_(0, 1, q);
             }
         } else if constexpr (MODE == LM_BYP) {
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-                const double nf[2] = {A_(0, p, 0), A_(1, p, 1)}, df[2] = {A_(1, p, 0), A_(0, p, 1)};
-                v[p] = group(nf, df);
+                num[p] = A_(0, p, 0) * A_(1, p, 1);
+                den[p] = A_(1, p, 0) * A_(0, p, 1);
             }
         } else if constexpr (MODE == LM_ALL) {
-            const double nf[4] = {A_(0, 0, 0), A_(1, 1, 0), A_(1, 0, 1), A_(0, 1, 1)};
-            const double df[4] = {A_(1, 0, 0), A_(0, 1, 0), A_(0, 0, 1), A_(1, 1, 1)};
-            v[0] = group(nf, df);
+            num[0] = (A_(0, 0, 0) * A_(1, 1, 0)) * (A_(1, 0, 1) * A_(0, 1, 1));
+            den[0] = (A_(1, 0, 0) * A_(0, 1, 0)) * (A_(0, 0, 1) * A_(1, 1, 1));
         }
 #undef A_
+    }
+    // true when some log argument of this family is exactly zero
+    FB_HD_M bool any_zero() const
+    {
+        bool z = false;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) z = z | (num[g] * den[g] == 0.0);
+        return z;
+    }
+    FB_HD_M void finish()
+    {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) v[g] = fm::log_ratio(num[g], den[g]);
     }
     // sum_{p,q} (-1)^(p+q) w[q][p] * lambda[q][p]
     FB_HD_M double wsum_full(const double (&w)[2][2]) const
@@ -180,27 +191,32 @@ struct AtanFam {
     }
 };
 
-// Rare pairs whose squared differences underflow: reference-order evaluation,
-// kept out of line so the hot loop stays small.
+// |d| < 2^-480 (zero, denormal, or so small that d*d leaves the range of the
+// branch-free root): exponent test on the ALU pipe.
+FB_HD bool tiny_or_zero(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
+
+// contribution of one pair to every requested component (before it is added
+// to the running sums): what the out-of-line careful variant hands back
+template <int NC>
+struct Contribution {
+    double v[NC];
+};
+
 template <uint32_t MASK>
 #if defined(__CUDACC__)
 __device__ __noinline__
 #else
 static
 #endif
-void pair_slow(double (&acc)[popc(MASK)], double xp, double yp, double zp, double x1, double x2,
-               double y1, double y2, double z1, double z2, double p0, double p1, double p2,
-               const double (&f)[3])
-{
-    pair_exact<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
-}
+Contribution<popc(MASK)> pair_careful(double xp, double yp, double zp, double x1, double x2,
+                                      double y1, double y2, double z1, double z2, double p0,
+                                      double p1, double p2, double f0, double f1, double f2);
 
-// |d| < 2^-480 (zero, denormal, or so small that d*d leaves the range of the
-// branch-free root): exponent test on the ALU pipe.
-FB_HD bool tiny_or_zero(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
-
-template <uint32_t MASK>
-FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
+// One pair.  CAREFUL = false: the hot path; returns false -- having added
+// nothing -- when the pair needs the special cases.  CAREFUL = true: applies
+// them, always returns true.  out[c] receives the pair's contribution.
+template <uint32_t MASK, bool CAREFUL>
+FB_HD bool pair_core(double (&out)[popc(MASK)], double xp, double yp, double zp,
                      double x1, double x2, double y1, double y2, double z1,
                      double z2, double p0, double p1, double p2,
                      const double (&f)[3])
@@ -236,22 +252,22 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
     const double XX[2] = {mul(X[0], X[0]), mul(X[1], X[1])};
     const double YY[2] = {mul(Y[0], Y[0]), mul(Y[1], Y[1])};
     const double ZZ[2] = {mul(Z[0], Z[0]), mul(Z[1], Z[1])};
-    // exact-zero / underflow detection (ALU pipe); the common case skips both
-    // fix-up blocks below
-    const bool tx[2] = {tiny_or_zero(X[0]), tiny_or_zero(X[1])};
-    const bool ty[2] = {tiny_or_zero(Y[0]), tiny_or_zero(Y[1])};
-    const bool tz[2] = {tiny_or_zero(Z[0]), tiny_or_zero(Z[1])};
-    const bool special = tx[0] | tx[1] | ty[0] | ty[1] | tz[0] | tz[1];
+    // exact zeros (and differences whose squares would underflow): ALU pipe
+    const bool special = tiny_or_zero(X[0]) | tiny_or_zero(X[1]) | tiny_or_zero(Y[0]) |
+                         tiny_or_zero(Y[1]) | tiny_or_zero(Z[0]) | tiny_or_zero(Z[1]);
     bool zx[2] = {false, false}, zy[2] = {false, false}, zz[2] = {false, false};
-    if (special) {
+    if constexpr (CAREFUL) {
         zx[0] = X[0] == 0.0; zx[1] = X[1] == 0.0;
         zy[0] = Y[0] == 0.0; zy[1] = Y[1] == 0.0;
         zz[0] = Z[0] == 0.0; zz[1] = Z[1] == 0.0;
-        if ((tx[0] & !zx[0]) | (tx[1] & !zx[1]) | (ty[0] & !zy[0]) | (ty[1] & !zy[1]) |
-            (tz[0] & !zz[0]) | (tz[1] & !zz[1])) {
+        if ((tiny_or_zero(X[0]) & !zx[0]) | (tiny_or_zero(X[1]) & !zx[1]) |
+            (tiny_or_zero(Y[0]) & !zy[0]) | (tiny_or_zero(Y[1]) & !zy[1]) |
+            (tiny_or_zero(Z[0]) & !zz[0]) | (tiny_or_zero(Z[1]) & !zz[1])) {
             // squares underflow: evaluate this pair the reference's way
-            pair_slow<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
-            return;
+#pragma unroll
+            for (int c = 0; c < popc(MASK); ++c) out[c] = 0.0;
+            pair_exact<MASK>(out, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
+            return true;
         }
     }
     double r[8];
@@ -262,9 +278,10 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
             const double sxy = add(XX[i], YY[j]);        // (dx**2 + dy**2) + dz**2
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const double r2 = add(sxy, ZZ[k]);
-                // on a vertex r2 == 0 and the branch-free root would give NaN
-                r[k * 4 + j * 2 + i] = (special && zx[i] && zy[j] && zz[k]) ? 0.0 : root(r2);
+                const double rr = root(add(sxy, ZZ[k]));
+                // on a vertex r2 == 0 and the branch-free root gives NaN
+                if constexpr (CAREFUL) r[k * 4 + j * 2 + i] = (zx[i] & zy[j] & zz[k]) ? 0.0 : rr;
+                else r[k * 4 + j * 2 + i] = rr;
             }
         }
 
@@ -281,6 +298,12 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
         if constexpr (MAX_ != AM_NONE) rex[c] = mul(absd(X[i]), r[c]);
         if constexpr (MAY_ != AM_NONE) rey[c] = mul(absd(Y[j]), r[c]);
         if constexpr (MAZ_ != AM_NONE) rez[c] = mul(absd(Z[k]), r[c]);
+        if constexpr (CAREFUL) {
+            // safe_atan2(0, 0) = 0 (_prism.pyx:16-26): unit factor
+            if constexpr (MAX_ != AM_NONE) if (zx[i] & (zy[j] | zz[k])) rex[c] = 1.0;
+            if constexpr (MAY_ != AM_NONE) if (zy[j] & (zx[i] | zz[k])) rey[c] = 1.0;
+            if constexpr (MAZ_ != AM_NONE) if (zz[k] & (zx[i] | zy[j])) rez[c] = 1.0;
+        }
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q)
@@ -291,49 +314,60 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
             if constexpr (MAZ_ != AM_NONE) imz[q * 2 + p] = mul(X[p], Y[q]);
         }
 
-    // ---- exact-zero differences: the reference's special cases --------------
+    LogFam<0, MLX> Lx;
+    LogFam<1, MLY> Ly;
+    LogFam<2, MLZ> Lz;
+    if constexpr (MLX != LM_NONE) Lx.template products<CAREFUL>(ax);
+    if constexpr (MLY != LM_NONE) Ly.template products<CAREFUL>(ay);
+    if constexpr (MLZ != LM_NONE) Lz.template products<CAREFUL>(az);
+
     double ex_xy = 0.0, ex_xz = 0.0, ex_yz = 0.0;   // shifted-r terms of gxy, gxz, gyz
-    if (special) {
+    if constexpr (!CAREFUL) {
+        bool bad = special;
+        if constexpr (MLX != LM_NONE) bad = bad | Lx.any_zero();
+        if constexpr (MLY != LM_NONE) bad = bad | Ly.any_zero();
+        if constexpr (MLZ != LM_NONE) bad = bad | Lz.any_zero();
+#if defined(__CUDA_ARCH__)
+        // warp vote: either every lane continues on the hot path or every lane
+        // re-evaluates carefully -- the warp never executes both
+        bad = __any_sync(0xffffffffu, bad);
+#endif
+        if (bad) return false;
+    } else {
+        // aligned with an edge on the far side: shifted r, gravity tensor only
+        // (_prism.pyx:327-330, :359-362, :418-421)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int i = c & 1, j = (c >> 1) & 1, k = c >> 2;
             const bool neg = (i + j + k) & 1;
-            // safe_atan2(0, 0) = 0: unit factor
-            if constexpr (MAX_ != AM_NONE) if (zx[i] & (zy[j] | zz[k])) rex[c] = 1.0;
-            if constexpr (MAY_ != AM_NONE) if (zy[j] & (zx[i] | zz[k])) rey[c] = 1.0;
-            if constexpr (MAZ_ != AM_NONE) if (zz[k] & (zx[i] | zy[j])) rez[c] = 1.0;
-            // aligned with an edge on the far side: shifted r (gravity tensor only)
             if constexpr (has_gxy) if (zx[i] & zy[j] & (Z[k] < 0.0)) {
                 const double t1 = mul(0.00001, sub(x2, x1)), t2 = mul(0.00001, sub(y2, y1));
-                const double L = safe_log_ref(add(Z[k], root(add(add(mul(t1, t1), mul(t2, t2)), ZZ[k]))));
+                const double L = safe_log_ref(add(Z[k], sqrt(add(add(mul(t1, t1), mul(t2, t2)), ZZ[k]))));
                 ex_xy += neg ? -L : L;
             }
             if constexpr (has_gxz) if (zx[i] & zz[k] & (Y[j] < 0.0)) {
                 const double t1 = mul(0.00001, sub(x2, x1)), t2 = mul(0.00001, sub(z2, z1));
-                const double L = safe_log_ref(add(Y[j], root(add(add(mul(t1, t1), mul(t2, t2)), YY[j]))));
+                const double L = safe_log_ref(add(Y[j], sqrt(add(add(mul(t1, t1), mul(t2, t2)), YY[j]))));
                 ex_xz += neg ? -L : L;
             }
             if constexpr (has_gyz) if (zy[j] & zz[k] & (X[i] < 0.0)) {
                 const double t1 = mul(0.00001, sub(y2, y1)), t2 = mul(0.00001, sub(z2, z1));
-                const double L = safe_log_ref(add(X[i], root(add(add(mul(t1, t1), mul(t2, t2)), XX[i]))));
+                const double L = safe_log_ref(add(X[i], sqrt(add(add(mul(t1, t1), mul(t2, t2)), XX[i]))));
                 ex_yz += neg ? -L : L;
             }
         }
     }
 
-    // ---- collapsed transcendental evaluation -----------------------------------
-    LogFam<0, MLX> Lx;
-    LogFam<1, MLY> Ly;
-    LogFam<2, MLZ> Lz;
+    // ---- collapsed transcendental evaluation: one straight-line block ---------
     AtanFam<0, MAX_> Ax;
     AtanFam<1, MAY_> Ay;
     AtanFam<2, MAZ_> Az;
     const bool nx[2] = {X[0] < 0.0, X[1] < 0.0};
     const bool ny[2] = {Y[0] < 0.0, Y[1] < 0.0};
     const bool nz[2] = {Z[0] < 0.0, Z[1] < 0.0};
-    if constexpr (MLX != LM_NONE) Lx.eval(ax);
-    if constexpr (MLY != LM_NONE) Ly.eval(ay);
-    if constexpr (MLZ != LM_NONE) Lz.eval(az);
+    if constexpr (MLX != LM_NONE) Lx.finish();
+    if constexpr (MLY != LM_NONE) Ly.finish();
+    if constexpr (MLZ != LM_NONE) Lz.finish();
     if constexpr (MAX_ != AM_NONE) Ax.eval(rex, imx, nx);
     if constexpr (MAY_ != AM_NONE) Ay.eval(rey, imy, ny);
     if constexpr (MAZ_ != AM_NONE) Az.eval(rez, imz, nz);
@@ -347,28 +381,21 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
             const double hx[2] = {0.5 * XX[0], 0.5 * XX[1]};
             const double hy[2] = {0.5 * YY[0], 0.5 * YY[1]};
             const double hz[2] = {0.5 * ZZ[0], 0.5 * ZZ[1]};
-            const double val = ((Lz.wsum_full(wxy) + Lx.wsum_full(wyz)) + Ly.wsum_full(wxz))
-                             - ((Ax.wsum_o(hx) + Ay.wsum_o(hy)) + Az.wsum_o(hz));
-            acc[c] = fma(val, p0, acc[c]); ++c;
+            out[c++] = (((Lz.wsum_full(wxy) + Lx.wsum_full(wyz)) + Ly.wsum_full(wxz))
+                        - ((Ax.wsum_o(hx) + Ay.wsum_o(hy)) + Az.wsum_o(hz))) * p0;
         }
-        if constexpr (has_gx) {       // :43-44
-            const double val = Ax.wsum_o(X) - (Lz.wsum_q(Y) + Ly.wsum_q(Z));
-            acc[c] = fma(val, p0, acc[c]); ++c;
-        }
-        if constexpr (has_gy) {       // :46-47
-            const double val = Ay.wsum_o(Y) - (Lx.wsum_q(Z) + Lz.wsum_p(X));
-            acc[c] = fma(val, p0, acc[c]); ++c;
-        }
-        if constexpr (has_gz) {       // :49-50
-            const double val = Az.wsum_o(Z) - (Ly.wsum_p(X) + Lx.wsum_p(Y));
-            acc[c] = fma(val, p0, acc[c]); ++c;
-        }
-        if constexpr (has_gxx) { acc[c] = fma(-Ax.all(), p0, acc[c]); ++c; }           // :52-53
-        if constexpr (has_gxy) { acc[c] = fma(Lz.all() + ex_xy, p0, acc[c]); ++c; }    // :55-56
-        if constexpr (has_gxz) { acc[c] = fma(Ly.all() + ex_xz, p0, acc[c]); ++c; }    // :58-59
-        if constexpr (has_gyy) { acc[c] = fma(-Ay.all(), p0, acc[c]); ++c; }           // :61-62
-        if constexpr (has_gyz) { acc[c] = fma(Lx.all() + ex_yz, p0, acc[c]); ++c; }    // :64-65
-        if constexpr (has_gzz) { acc[c] = fma(-Az.all(), p0, acc[c]); ++c; }           // :67-68
+        if constexpr (has_gx)         // :43-44
+            out[c++] = (Ax.wsum_o(X) - (Lz.wsum_q(Y) + Ly.wsum_q(Z))) * p0;
+        if constexpr (has_gy)         // :46-47
+            out[c++] = (Ay.wsum_o(Y) - (Lx.wsum_q(Z) + Lz.wsum_p(X))) * p0;
+        if constexpr (has_gz)         // :49-50
+            out[c++] = (Az.wsum_o(Z) - (Ly.wsum_p(X) + Lx.wsum_p(Y))) * p0;
+        if constexpr (has_gxx) out[c++] = -Ax.all() * p0;              // :52-53
+        if constexpr (has_gxy) out[c++] = (Lz.all() + ex_xy) * p0;     // :55-56
+        if constexpr (has_gxz) out[c++] = (Ly.all() + ex_xz) * p0;     // :58-59
+        if constexpr (has_gyy) out[c++] = -Ay.all() * p0;              // :61-62
+        if constexpr (has_gyz) out[c++] = (Lx.all() + ex_yz) * p0;     // :64-65
+        if constexpr (has_gzz) out[c++] = -Az.all() * p0;              // :67-68
     } else {
         // second derivatives of the 1/r volume integral, summed over corners
         // (v1..v6 of _prism.pyx:94-99); unused ones are never evaluated
@@ -382,11 +409,47 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
         const double bx = fma(vxx, p0, fma(vxy, p1, vxz * p2));   // :100
         const double by = fma(vxy, p0, fma(vyy, p1, vyz * p2));   // :101
         const double bz = fma(vxz, p0, fma(vyz, p1, vzz * p2));   // :102
-        if constexpr (has_tf) { acc[c] += fma(f[0], bx, fma(f[1], by, f[2] * bz)); ++c; }  // :103
-        if constexpr (has_bx) { acc[c] += bx; ++c; }
-        if constexpr (has_by) { acc[c] += by; ++c; }
-        if constexpr (has_bz) { acc[c] += bz; ++c; }
+        if constexpr (has_tf) out[c++] = fma(f[0], bx, fma(f[1], by, f[2] * bz));   // :103
+        if constexpr (has_bx) out[c++] = bx;
+        if constexpr (has_by) out[c++] = by;
+        if constexpr (has_bz) out[c++] = bz;
     }
+    (void)ex_xy; (void)ex_xz; (void)ex_yz; (void)special;
+    return true;
+}
+
+template <uint32_t MASK>
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+static
+#endif
+Contribution<popc(MASK)> pair_careful(double xp, double yp, double zp, double x1, double x2,
+                                      double y1, double y2, double z1, double z2, double p0,
+                                      double p1, double p2, double f0, double f1, double f2)
+{
+    Contribution<popc(MASK)> res;
+    const double f[3] = {f0, f1, f2};
+    pair_core<MASK, true>(res.v, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f);
+    return res;
+}
+
+template <uint32_t MASK>
+FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
+                     double x1, double x2, double y1, double y2, double z1,
+                     double z2, double p0, double p1, double p2,
+                     const double (&f)[3])
+{
+    constexpr int NC = popc(MASK);
+    double out[NC];
+    if (!pair_core<MASK, false>(out, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f)) {
+        const Contribution<NC> res =
+            pair_careful<MASK>(xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f[0], f[1], f[2]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) out[c] = res.v[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] += out[c];
 }
 
 struct EvalFast {
