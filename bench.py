@@ -53,7 +53,7 @@ WORK = {
 }
 # FP64-pipe instructions the fast kernels actually execute per pair (ncu
 # smsp__inst_executed_pipe_fp64 / pairs, see profiles/); None until measured.
-EXECUTED_FP64_PER_PAIR = {"c2": None, "c3": None, "c4": None, "c5": None, "c5t": None}
+EXECUTED_FP64_PER_PAIR = {"c2": 426.4, "c3": 435.7, "c4": 365.0, "c5": 311.3, "c5t": 513.0}   # profiles/r01a_*
 
 
 # --------------------------------------------------------------------------
@@ -380,7 +380,7 @@ def run_gpu(args):
                                    % (burst.value, sustained.value),
                     "algorithmic_flop_per_pair": wk['flop'], "algorithmic_of": wk['what'],
                     "executed_fp64_inst_per_pair": executed,
-                    "executed_frac": (per_gpu * executed / (148 * 32 * sm_hz / 2.0 * 1.0)
+                    "executed_frac": (per_gpu * executed / (148 * 64 * sm_hz)
                                       if executed else None)}
         if w['kind'] == 'jacobian':
             peaks = {}

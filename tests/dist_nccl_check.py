@@ -1,0 +1,51 @@
+"""
+Multi-GPU check of the partitioner under NCCL (run with torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_nccl_check.py
+
+Observation sharding must reproduce the single-GPU result bit for bit (list-order
+summation); prism sharding (one NCCL all-reduce) to rounding.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from fatiando_b200 import mesher, gridder, partition, prism
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rs = np.random.RandomState(3)
+    mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (6, 20, 20))
+    mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+    xp, yp, zp = gridder.regular((0, 5000, 0, 5000), (60, 50), z=-150)
+    names = ['gz', 'gxx', 'gxy', 'gzz']
+    with prism.Model(mesh, 'density', device=local) as model:
+        full = model.fields(xp, yp, zp, names, list_order=True)
+    obs = partition.fields_observation_sharded(xp, yp, zp, mesh, names, device=local,
+                                               list_order=True)
+    pri = partition.fields_prism_sharded(xp, yp, zp, mesh, names, device=local)
+    ok = True
+    for nm in names:
+        ok &= bool(np.array_equal(obs[nm], full[nm]))
+        scale = np.abs(full[nm]).max()
+        ok &= bool(np.allclose(pri[nm], full[nm], rtol=1e-10, atol=1e-12 * scale))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("dist_nccl_check world=%d: %s" % (world, "OK" if flag.item() == 1 else "MISMATCH"))
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -340,3 +340,32 @@ def test_input_contract(gpu_lib):
     assert prism.gz(np.zeros(0), np.zeros(0), np.zeros(0), model).shape == (0,)
     nan = prism.gz(np.array([np.nan]), np.array([0.0]), np.array([-1.0]), model)
     assert np.isnan(nan[0])
+
+
+def test_multi_gpu_sharding_under_nccl(gpu_lib):
+    """One rank per visible GPU (at most 2 here); world 1 still exercises the NCCL path."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    n = min(2, gpu_lib.device_count())
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29511",
+           os.path.join(ROOT, "tests", "dist_nccl_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "OK" in res.stdout
+
+
+def test_single_process_multi_device(gpu_lib):
+    from fatiando_b200 import prism, mesher, gridder, partition
+    rs = np.random.RandomState(3)
+    mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (4, 10, 10))
+    mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+    xp, yp, zp = gridder.regular((0, 5000, 0, 5000), (31, 17), z=-150)
+    devices = list(range(gpu_lib.device_count())) * 2          # also >1 shard on one GPU
+    got = partition.fields_multi_device(xp, yp, zp, mesh, ['gz', 'gyz'], devices, list_order=True)
+    with prism.Model(mesh, 'density') as model:
+        want = model.fields(xp, yp, zp, ['gz', 'gyz'], list_order=True)
+    for nm in want:
+        assert np.array_equal(got[nm], want[nm])

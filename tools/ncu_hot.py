@@ -48,4 +48,7 @@ def main(path, pairs=None):
 
 
 if __name__ == '__main__':
-    main(*sys.argv[1:])
+    try:
+        main(*sys.argv[1:])
+    except BrokenPipeError:
+        pass
