@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfatiando_b200.so")
+# FB200_LIBRARY selects another build of the same ABI (kernel tuning experiments)
+LIB_PATH = os.environ.get("FB200_LIBRARY") or os.path.join(HERE, "libfatiando_b200.so")
 
 OK, EINVAL, ECUDA, EPROP, EUNSUP = 0, -1, -2, -3, -4
 DEVICE_POINTERS, REFERENCE_ORDER, TRANSPOSED, NO_PRISM_SPLIT = 1, 2, 4, 8

@@ -43,7 +43,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, jobs=None, verbose=False):
+def build(force=False, jobs=None, verbose=False, extra_flags=(), tag=""):
+    """tag/extra_flags build an experimental variant next to the product library."""
+    global BUILD, LIB
+    if tag:
+        BUILD = os.path.join(HERE, "build_" + tag)
+        LIB = os.path.join(HERE, "libfatiando_b200_%s.so" % tag)
     os.makedirs(BUILD, exist_ok=True)
     headers = (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))
                + glob.glob(os.path.join(INCLUDE, "*.h")) + [os.path.abspath(__file__)])
@@ -53,7 +58,7 @@ def build(force=False, jobs=None, verbose=False):
         obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            flags = list(COMMON)
+            flags = list(COMMON) + list(extra_flags)
             if src.endswith("_exact.cu"):
                 flags.append("-fmad=false")
             if verbose:
@@ -77,4 +82,6 @@ def build(force=False, jobs=None, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    tag = next((a[6:] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=extra, tag=tag))

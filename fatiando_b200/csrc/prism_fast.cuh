@@ -146,34 +146,35 @@ struct LogFam {
     }
 };
 
-// sum of s*safe_atan2(im, re) with re = |own coordinate| * r, grouped by own axis
+// sum of s*safe_atan2(im, x*r) grouped by the own axis.  re[c] = x_o * r_c with
+// the sign of x_o (the folding of atan2 to (-pi/2, pi/2] is done by the sign
+// bookkeeping of Wind); im[q*2+p] = product of the two other coordinates;
+// hown[o] = high word of the own coordinate x_o.
 template <int OWN, AtanMode MODE>
 struct AtanFam {
     double v[2];
 
-    // re[c]: |C_o| * r_c ; im[q*2+p]: product of the two other coordinates ;
-    // negown[o]: own coordinate < 0 (flips the sign of the folded arctangent)
-    FB_HD_M void eval(const double (&re)[8], const double (&im)[4], const bool (&negown)[2])
+    FB_HD_M void eval(const double (&re)[8], const double (&im)[4], const int (&hown)[2])
     {
         using namespace fm;
         if constexpr (MODE == AM_BYOWN) {
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
-                Wind w = wind_start(re[cidx<OWN>(o, 0, 0)], neg_if(im[0], negown[o]));
-                wind_mul(w, re[cidx<OWN>(o, 1, 0)], neg_if(im[1], !negown[o]));
-                wind_mul(w, re[cidx<OWN>(o, 0, 1)], neg_if(im[2], !negown[o]));
-                wind_mul(w, re[cidx<OWN>(o, 1, 1)], neg_if(im[3], negown[o]));
+                Wind w = wind_start<false>(re[cidx<OWN>(o, 0, 0)], im[0]);
+                wind_mul<true>(w, re[cidx<OWN>(o, 1, 0)], im[1], hown[o]);
+                wind_mul<true>(w, re[cidx<OWN>(o, 0, 1)], im[2], hown[o]);
+                wind_mul<false>(w, re[cidx<OWN>(o, 1, 1)], im[3], hown[o]);
                 v[o] = wind_angle(w);
             }
         } else if constexpr (MODE == AM_ALL) {
-            Wind w = wind_start(re[cidx<OWN>(0, 0, 0)], neg_if(im[0], negown[0]));
-            wind_mul(w, re[cidx<OWN>(0, 1, 0)], neg_if(im[1], !negown[0]));
-            wind_mul(w, re[cidx<OWN>(0, 0, 1)], neg_if(im[2], !negown[0]));
-            wind_mul(w, re[cidx<OWN>(0, 1, 1)], neg_if(im[3], negown[0]));
-            wind_mul(w, re[cidx<OWN>(1, 0, 0)], neg_if(im[0], !negown[1]));
-            wind_mul(w, re[cidx<OWN>(1, 1, 0)], neg_if(im[1], negown[1]));
-            wind_mul(w, re[cidx<OWN>(1, 0, 1)], neg_if(im[2], negown[1]));
-            wind_mul(w, re[cidx<OWN>(1, 1, 1)], neg_if(im[3], !negown[1]));
+            Wind w = wind_start<false>(re[cidx<OWN>(0, 0, 0)], im[0]);
+            wind_mul<true>(w, re[cidx<OWN>(0, 1, 0)], im[1], hown[0]);
+            wind_mul<true>(w, re[cidx<OWN>(0, 0, 1)], im[2], hown[0]);
+            wind_mul<false>(w, re[cidx<OWN>(0, 1, 1)], im[3], hown[0]);
+            wind_mul<true>(w, re[cidx<OWN>(1, 0, 0)], im[0], hown[1]);
+            wind_mul<false>(w, re[cidx<OWN>(1, 1, 0)], im[1], hown[1]);
+            wind_mul<false>(w, re[cidx<OWN>(1, 0, 1)], im[2], hown[1]);
+            wind_mul<true>(w, re[cidx<OWN>(1, 1, 1)], im[3], hown[1]);
             v[0] = wind_angle(w);
         }
     }
@@ -246,9 +247,15 @@ FB_HD bool pair_core(double (&out)[popc(MASK)], double xp, double yp, double zp,
                                   : atan_mode(has_pot || has_gz, has_gzz);
 
     // integration limits, index 0 <-> the "2" bound (_prism.pyx:82-84,88-92)
-    const double X[2] = {sub(x2, xp), sub(x1, xp)};
-    const double Y[2] = {sub(y2, yp), sub(y1, yp)};
-    const double Z[2] = {sub(z2, zp), sub(z1, zp)};
+    double X[2] = {sub(x2, xp), sub(x1, xp)};
+    double Y[2] = {sub(y2, yp), sub(y1, yp)};
+    double Z[2] = {sub(z2, zp), sub(z1, zp)};
+    if constexpr (CAREFUL) {
+        // the sign bookkeeping below reads sign BITS; the reference's tests are
+        // `< 0`, false for -0.0: make exact zeros +0.0
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { X[t] = add(X[t], 0.0); Y[t] = add(Y[t], 0.0); Z[t] = add(Z[t], 0.0); }
+    }
     const double XX[2] = {mul(X[0], X[0]), mul(X[1], X[1])};
     const double YY[2] = {mul(Y[0], Y[0]), mul(Y[1], Y[1])};
     const double ZZ[2] = {mul(Z[0], Z[0]), mul(Z[1], Z[1])};
@@ -287,7 +294,7 @@ FB_HD bool pair_core(double (&out)[popc(MASK)], double xp, double yp, double zp,
 
     // ---- arguments, with the reference's roundings -------------------------
     double ax[8], ay[8], az[8];          // x + r, y + r, z + r
-    double rex[8], rey[8], rez[8];       // |x|*r, |y|*r, |z|*r
+    double rex[8], rey[8], rez[8];       // x*r, y*r, z*r
     double imx[4], imy[4], imz[4];       // z*y [k][j], z*x [k][i], x*y [j][i]  (q*2+p)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -295,9 +302,9 @@ FB_HD bool pair_core(double (&out)[popc(MASK)], double xp, double yp, double zp,
         if constexpr (MLX != LM_NONE) ax[c] = add(X[i], r[c]);
         if constexpr (MLY != LM_NONE) ay[c] = add(Y[j], r[c]);
         if constexpr (MLZ != LM_NONE) az[c] = add(Z[k], r[c]);
-        if constexpr (MAX_ != AM_NONE) rex[c] = mul(absd(X[i]), r[c]);
-        if constexpr (MAY_ != AM_NONE) rey[c] = mul(absd(Y[j]), r[c]);
-        if constexpr (MAZ_ != AM_NONE) rez[c] = mul(absd(Z[k]), r[c]);
+        if constexpr (MAX_ != AM_NONE) rex[c] = mul(X[i], r[c]);
+        if constexpr (MAY_ != AM_NONE) rey[c] = mul(Y[j], r[c]);
+        if constexpr (MAZ_ != AM_NONE) rez[c] = mul(Z[k], r[c]);
         if constexpr (CAREFUL) {
             // safe_atan2(0, 0) = 0 (_prism.pyx:16-26): unit factor
             if constexpr (MAX_ != AM_NONE) if (zx[i] & (zy[j] | zz[k])) rex[c] = 1.0;
@@ -362,15 +369,15 @@ FB_HD bool pair_core(double (&out)[popc(MASK)], double xp, double yp, double zp,
     AtanFam<0, MAX_> Ax;
     AtanFam<1, MAY_> Ay;
     AtanFam<2, MAZ_> Az;
-    const bool nx[2] = {X[0] < 0.0, X[1] < 0.0};
-    const bool ny[2] = {Y[0] < 0.0, Y[1] < 0.0};
-    const bool nz[2] = {Z[0] < 0.0, Z[1] < 0.0};
+    const int hx[2] = {hi32(X[0]), hi32(X[1])};
+    const int hy[2] = {hi32(Y[0]), hi32(Y[1])};
+    const int hz[2] = {hi32(Z[0]), hi32(Z[1])};
     if constexpr (MLX != LM_NONE) Lx.finish();
     if constexpr (MLY != LM_NONE) Ly.finish();
     if constexpr (MLZ != LM_NONE) Lz.finish();
-    if constexpr (MAX_ != AM_NONE) Ax.eval(rex, imx, nx);
-    if constexpr (MAY_ != AM_NONE) Ay.eval(rey, imy, ny);
-    if constexpr (MAZ_ != AM_NONE) Az.eval(rez, imz, nz);
+    if constexpr (MAX_ != AM_NONE) Ax.eval(rex, imx, hx);
+    if constexpr (MAY_ != AM_NONE) Ay.eval(rey, imy, hy);
+    if constexpr (MAZ_ != AM_NONE) Az.eval(rez, imz, hz);
 
     int c = 0;
     if constexpr (!MAG) {

@@ -19,8 +19,15 @@
 namespace fb200 {
 
 // Eval::template pair<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f)
+// 4 resident blocks (16 warps) per SM = a 128-register budget.  Measured on B200:
+// 3, 4, 5 or 6 blocks differ by < 2 % (the kernels are bound by instruction
+// issue, not by latency hiding), 4 is marginally best for the 6-7 component sets.
+#ifndef FB200_FWD_MIN_BLOCKS
+#define FB200_FWD_MIN_BLOCKS 4
+#endif
+
 template <uint32_t MASK, class Eval>
-__global__ void __launch_bounds__(FWD_THREADS)
+__global__ void __launch_bounds__(FWD_THREADS, FB200_FWD_MIN_BLOCKS)
 forward_kernel(const ForwardArgs a)
 {
     constexpr int NC = popc(MASK);
