@@ -116,19 +116,26 @@ __global__ void fill_kernel(double *p, int64_t n, double v)
     if (i < n) p[i] = v;
 }
 
-// 8 independent DFMA chains per thread, everything in registers.
+// 8 independent DFMA chains per thread, everything in registers.  Operand mix
+// register, register, uniform: the fastest of the mixes probed on B200
+// (tools/fp64_pipe_probe.cu: 99 % of 148 SM x 64 lanes x clock; register,
+// uniform, uniform only reaches 91 %), so this is the true pipe ceiling.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
 {
-    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4,
-           x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    double x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { x[k] = threadIdx.x * 1e-3 + k; y[k] = a + 1e-12 * (threadIdx.x + k); }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = fma(x[k], y[k], b);
         }
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 __global__ void debug_math_kernel(int op, const double *a, const double *b, int64_t n, double *out)
