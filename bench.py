@@ -46,6 +46,7 @@ UNIT = "pairs/s"
 # formulation fused into one pass (FLOP, DFMA = 2) and FP64-pipe slots.
 WORK = {
     "c2": dict(flop=2802.0, slots=1922.0, what="6 tensor components"),
+    "c2a": dict(flop=2802.0, slots=1922.0, what="6 tensor components"),
     "c3": dict(flop=2820.0, slots=1940.0, what="tf+bx+by+bz"),
     "c4": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
     "c5": dict(flop=1478.0, slots=1022.0, what="gz"),
@@ -53,7 +54,9 @@ WORK = {
 }
 # FP64-pipe instructions the fast kernels actually execute per pair (ncu
 # smsp__inst_executed_pipe_fp64 / pairs, see profiles/); None until measured.
-EXECUTED_FP64_PER_PAIR = {"c2": 426.4, "c3": 435.7, "c4": 365.0, "c5": 311.3, "c5t": 513.0}   # profiles/r01a_*
+# c4: the Jacobian kernel runs the same pair evaluator as c5; the profiled first row block
+# executes 373 because 2/3 of its rows lie on mesh planes (careful variant), see profiles/.
+EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3}   # profiles/r01_*
 
 
 # --------------------------------------------------------------------------
@@ -70,6 +73,13 @@ def make_workload(name, world=1):
                     xp=xp, yp=yp, zp=zp, fvec=None, kind='forward',
                     label="C2: gxx..gzz of PrismMesh 50x50x20 (5e4 prisms, variable density) on a "
                           "%dx200 grid at z=-150" % (200 * world))
+    if name == "c2a":
+        # C2 with the grid ON the mesh planes (spacing 25 m, cells 100 m): every 4th
+        # grid line coincides with cell faces -- the common "aligned" user setup
+        w = make_workload("c2", world)
+        w['xp'], w['yp'], w['zp'] = gridder.regular((0, 5000, 0, 5000), (201 * world, 201), z=-150)
+        w['label'] = "C2 aligned: gxx..gzz of PrismMesh 50x50x20 on a %dx201 grid whose lines hit cell faces" % (201 * world)
+        return w
     if name == "c3":
         mesh = mesher.PrismMesh((0, 10000, 0, 10000, 0, 2000), (10, 100, 100))
         inc, dec = 30, -15

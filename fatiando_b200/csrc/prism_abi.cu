@@ -110,6 +110,15 @@ __global__ void reduce_partials_kernel(const ReduceArgs a)
     a.out[(int64_t)a.out_row[c] * a.ld_out + l] = s * a.scale[c];
 }
 
+// -0.0 -> +0.0 in the model bounds: the fast path reads sign BITS of coordinate
+// differences where the reference tests `< 0` (false for -0.0); with canonical
+// bounds a difference can only be -0.0 if it is a genuine negative underflow.
+__global__ void canonical_zero_kernel(double *p, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = p[i] + 0.0;
+}
+
 __global__ void fill_kernel(double *p, int64_t n, double v)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,7 +269,10 @@ extern "C" int fb200_model_create(int device, int64_t m, const double *x1, const
     CKM(cuda_rc(cudaStreamCreateWithFlags(&mod->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
     CKM(cuda_rc(cudaEventCreate(&mod->ev0), "cudaEventCreate"));
     CKM(cuda_rc(cudaEventCreate(&mod->ev1), "cudaEventCreate"));
-    for (int r = 0; r < 6; ++r) CKM(upload(&mod->d_b[r], src[r], m, m_pad, mod->stream));
+    for (int r = 0; r < 6; ++r) {
+        CKM(upload(&mod->d_b[r], src[r], m, m_pad, mod->stream));
+        canonical_zero_kernel<<<(unsigned)((m_pad + 255) / 256), 256, 0, mod->stream>>>(mod->d_b[r], m_pad);
+    }
     if (density) CKM(upload(&mod->d_dens, density, m, m_pad, mod->stream));
     if (nmag == 3) {
         CKM(upload(&mod->d_mag[0], mx, m, m_pad, mod->stream));

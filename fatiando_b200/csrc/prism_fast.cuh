@@ -11,9 +11,9 @@
 //   * the 1e-5*size shift of r for gxy/gxz/gyz when the point is aligned with
 //     an edge on the far side (:327-330, :359-362, :418-421) -- and NOT for
 //     tf/bx/by/bz, which use the unshifted kernels (:94-99).
-// They only matter when a coordinate difference is exactly zero or a log
-// argument rounds to exactly zero (point on, or within ~1e-8 relative of, the
-// extension of an edge).  The hot path carries none of that: it detects those
+// They only matter when coordinate differences are exactly zero on two axes
+// at once, or a log argument rounds to exactly zero (point on, or within ~1e-8
+// relative of, the line through an edge).  The hot path carries none of that: it detects those
 // pairs with a handful of ALU-pipe tests and two compares per log group, and
 // if ANY lane of the warp has one (warp vote, so the warp never diverges) the
 // whole warp re-evaluates the pair with the out-of-line "careful" variant,
@@ -259,9 +259,15 @@ FB_HD bool pair_core(double (&out)[popc(MASK)], double xp, double yp, double zp,
     const double XX[2] = {mul(X[0], X[0]), mul(X[1], X[1])};
     const double YY[2] = {mul(Y[0], Y[0]), mul(Y[1], Y[1])};
     const double ZZ[2] = {mul(Z[0], Z[0]), mul(Z[1], Z[1])};
-    // exact zeros (and differences whose squares would underflow): ALU pipe
-    const bool special = tiny_or_zero(X[0]) | tiny_or_zero(X[1]) | tiny_or_zero(Y[0]) |
-                         tiny_or_zero(Y[1]) | tiny_or_zero(Z[0]) | tiny_or_zero(Z[1]);
+    // Exact zeros (and differences whose squares would underflow), ALU pipe.  A
+    // zero on ONE axis is harmless on the hot path (r > 0, every complex factor
+    // is non-zero, signs are those of +0.0 because the model bounds are
+    // canonicalised at upload); the special cases need zeros on two axes at once
+    // (point on the line through an edge, or on a vertex).
+    const bool sx = tiny_or_zero(X[0]) | tiny_or_zero(X[1]);
+    const bool sy = tiny_or_zero(Y[0]) | tiny_or_zero(Y[1]);
+    const bool sz = tiny_or_zero(Z[0]) | tiny_or_zero(Z[1]);
+    const bool special = (sx & sy) | (sx & sz) | (sy & sz);
     bool zx[2] = {false, false}, zy[2] = {false, false}, zz[2] = {false, false};
     if constexpr (CAREFUL) {
         zx[0] = X[0] == 0.0; zx[1] = X[1] == 0.0;

@@ -323,6 +323,30 @@ def test_size_independent_properties_at_scale(gpu_lib):
     np.testing.assert_allclose(t2, 2.0 * t['gzz'], rtol=1e-12, atol=1e-12 * scale)
 
 
+def test_negative_zero_bounds_and_points_on_planes(gpu_lib, oracle):
+    """-0.0 bounds (e.g. z = -1*0.0 from a flat relief) with points in those planes:
+    the reference tests `x < 0`, false for -0.0; the kernel reads sign bits, so the
+    upload canonicalises zeros."""
+    from fatiando_b200 import prism
+    from fatiando_b200.flatten import FlatModel
+    nz = -0.0
+    b = [np.array([nz, -50.0, 10.0]), np.array([100.0, nz, 60.0]),
+         np.array([nz, -30.0, nz]), np.array([80.0, nz, 40.0]),
+         np.array([nz, nz, 5.0]), np.array([60.0, 70.0, 25.0])]
+    dens = np.array([1000.0, -700.0, 300.0])
+    xp = np.array([0.0, -0.0, 30.0, 0.0, 100.0, 12.0, 0.0, -20.0])
+    yp = np.array([5.0, 40.0, 0.0, -0.0, 80.0, -0.0, 0.0, 0.0])
+    zp = np.array([0.0, -0.0, -3.0, 0.0, 0.0, -1.0, -7.0, 0.0])
+    flat = FlatModel(b, dens, None, np.arange(3), 3)
+    names = ['potential', 'gx', 'gy', 'gz', 'gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz']
+    with prism.Model(flat, 'density') as model:
+        res = model.fields(xp, yp, zp, names)
+    for f in names:
+        ref = oracle.model(f, xp, yp, zp, b, dens[:, None])
+        cond = oracle.condition(f, xp, yp, zp, b, dens[:, None])
+        assert_parity(res[f], ref, cond, C_FLOOR_FAST, 'negative zero ' + f)
+
+
 def test_input_contract(gpu_lib):
     from fatiando_b200 import prism, mesher
     model = [mesher.Prism(0, 1, 0, 1, 0, 1, {'density': 1.0})]
