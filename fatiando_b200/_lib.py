@@ -45,6 +45,9 @@ _SIGNATURES = {
     "fb200_jacobian": ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64,
                         ctypes.c_int, _dp, _dp, _d, ctypes.c_void_p, _i64, ctypes.c_uint32],
                        ctypes.c_int),
+    "fb200_adjoint": ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _i64,
+                       ctypes.c_int, _dp, _dp, _d, ctypes.c_void_p, ctypes.c_void_p,
+                       ctypes.c_uint32], ctypes.c_int),
     "fb200_set_default_device": ([ctypes.c_int], ctypes.c_int),
     "fb200_prism_tf": ([_dp, _dp, _dp, _i64] + [_d] * 12 + [_dp], ctypes.c_int),
     "fb200_prism_bx": ([_dp, _dp, _dp, _i64] + [_d] * 9 + [_dp], ctypes.c_int),

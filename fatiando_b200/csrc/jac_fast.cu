@@ -16,4 +16,15 @@ cudaError_t launch_jacobian_fast(int field, bool transposed, const JacobianArgs 
     }
 }
 
+cudaError_t launch_adjoint_fast(int field, const AdjointArgs &a, int nsplit, cudaStream_t s)
+{
+    switch (field) {
+#define CASE(F) case F: return launch_adjoint_t<(1u << F), EvalFast>(a, nsplit, s);
+        CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+        CASE(10) CASE(11) CASE(12) CASE(13)
+#undef CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace fb200

@@ -601,6 +601,99 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
 }
 
 // ---------------------------------------------------------------------------
+// adjoint J^T d (imaging.py:116-118), never storing J
+// ---------------------------------------------------------------------------
+extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *yp,
+                             const double *zp, int64_t n, int field, const double *unit_prop,
+                             const double *fvec, double scale, const double *data, double *out,
+                             uint32_t flags)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    if (n < 0) return fail(FB200_EINVAL, "negative point count");
+    if (field < 0 || field >= F_COUNT) return fail(FB200_EINVAL, "invalid field id");
+    if (!unit_prop) return fail(FB200_EINVAL, "unit_prop is NULL");
+    if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER))
+        return fail(FB200_EUNSUP, "unsupported flag for fb200_adjoint");
+    const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
+    const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
+    const int64_t m = mod->m;
+    if (m == 0) return FB200_OK;
+    if (!out || (n > 0 && (!xp || !yp || !zp || !data))) return fail(FB200_EINVAL, "NULL array");
+    const bool magnetic = field >= F_TF;
+
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    mod->last_launches = 0;
+    mod->last_ms = 0.0;
+
+    const double *d_xp = xp, *d_yp = yp, *d_zp = zp, *d_w = data;
+    double *d_out = out;
+    const int64_t mp = (m + 31) / 32 * 32;
+    if (!on_device) {
+        const int64_t np = (n + 31) / 32 * 32;
+        int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 4 + 32);
+        if (rc != FB200_OK) return rc;
+        rc = grow(&mod->d_out, &mod->out_cap, (size_t)mp);
+        if (rc != FB200_OK) return rc;
+        if (n > 0) {
+            CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+            CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+            CK(cudaMemcpyAsync(mod->d_pts + 2 * np, zp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+            CK(cudaMemcpyAsync(mod->d_pts + 3 * np, data, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+        }
+        d_xp = mod->d_pts; d_yp = mod->d_pts + np; d_zp = mod->d_pts + 2 * np; d_w = mod->d_pts + 3 * np;
+        d_out = mod->d_out;
+    }
+    if (n == 0) {
+        fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, mod->stream>>>(d_out, m, 0.0);
+        CK(cudaGetLastError());
+    } else {
+        // split the points so that every SM has work even for small models
+        const int64_t blocks_x = (m + JAC_THREADS - 1) / JAC_THREADS;
+        const int64_t tiles = (n + JAC_TILE - 1) / JAC_TILE;
+        int64_t nsplit = std::min<int64_t>(
+            std::max<int64_t>(1, ((int64_t)mod->sm_count * 20 + blocks_x - 1) / blocks_x), tiles);
+        nsplit = std::min<int64_t>(nsplit, 65535);
+        const int64_t rows = ((tiles + nsplit - 1) / nsplit) * JAC_TILE;
+        nsplit = (n + rows - 1) / rows;
+        int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * mp);
+        if (rc != FB200_OK) return rc;
+        AdjointArgs a;
+        std::memset(&a, 0, sizeof(a));
+        view_of(mod, magnetic, &a.j.model);
+        for (int r = 0; r < 3; ++r) a.j.unit_p[r] = magnetic ? unit_prop[r] : (r == 0 ? unit_prop[0] : 0.0);
+        for (int r = 0; r < 3; ++r) a.j.fvec[r] = fvec ? fvec[r] : 0.0;
+        a.j.xp = d_xp; a.j.yp = d_yp; a.j.zp = d_zp; a.j.n = n;
+        a.weights = d_w;
+        a.part = mod->d_part;
+        a.ld_p = mp;
+        a.rows_per_split = rows;
+        CK(cudaEventRecord(mod->ev0, mod->stream));
+        CK(exact ? launch_adjoint_exact(field, a, (int)nsplit, mod->stream)
+                 : launch_adjoint_fast(field, a, (int)nsplit, mod->stream));
+        ReduceArgs r;
+        std::memset(&r, 0, sizeof(r));
+        r.part = mod->d_part; r.out = d_out; r.n = m; r.ld = mp; r.ld_out = mp;
+        r.nc = 1; r.nsplit = (int)nsplit; r.scale[0] = scale; r.out_row[0] = 0;
+        reduce_partials_kernel<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, mod->stream>>>(r);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(mod->ev1, mod->stream));
+        mod->last_launches = 2;
+    }
+    if (!on_device)
+        CK(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, mod->stream));
+    CK(cudaStreamSynchronize(mod->stream));
+    if (n > 0) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+        mod->last_ms = ms;
+    }
+    return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------
 // the reference's own FFI shape: one prism accumulated into res
 // ---------------------------------------------------------------------------
 static int g_default_device = 0;

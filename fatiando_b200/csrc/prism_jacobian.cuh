@@ -97,6 +97,65 @@ jacobian_t_kernel(const JacobianArgs a)
     }
 }
 
+// ---- adjoint: out[q] = sum_l d[l] * field(point l, prism q, unit property) -----
+// J^T d without ever storing J -- what imaging.py:116-118 computes per layer as
+// dot(sensibility_T, gz).  Lane <-> prism as in jacobian_kernel; blockIdx.y
+// walks a contiguous range of point tiles; partial sums per range go to scratch
+// and are added in range order by reduce_partials_kernel.
+struct AdjointArgs {
+    JacobianArgs j;          // model, points, unit property, fvec (scale/out/ld unused)
+    const double *weights;   // d[l]
+    double *part;            // [nsplit][ld_p]
+    int64_t ld_p;
+    int64_t rows_per_split;  // multiple of JAC_TILE
+};
+
+template <uint32_t MASK, class Eval>
+__global__ void __launch_bounds__(JAC_THREADS)
+adjoint_kernel(const AdjointArgs a)
+{
+    static_assert(popc(MASK) == 1, "one field per adjoint");
+    __shared__ double pts[4][JAC_TILE];
+    const ModelView &mv = a.j.model;
+    int64_t q = (int64_t)blockIdx.x * JAC_THREADS + threadIdx.x;
+    const bool active = q < mv.m;
+    if (!active) q = mv.m - 1;
+    const double x1 = mv.b[0][q], x2 = mv.b[1][q], y1 = mv.b[2][q], y2 = mv.b[3][q],
+                 z1 = mv.b[4][q], z2 = mv.b[5][q];
+    const double f[3] = {a.j.fvec[0], a.j.fvec[1], a.j.fvec[2]};
+    const double u0 = a.j.unit_p[0], u1 = a.j.unit_p[1], u2 = a.j.unit_p[2];
+    const int64_t l_begin = (int64_t)blockIdx.y * a.rows_per_split;
+    const int64_t l_end = (l_begin + a.rows_per_split < a.j.n) ? l_begin + a.rows_per_split : a.j.n;
+    double acc[1] = {0.0};
+    for (int64_t l0 = l_begin; l0 < l_end; l0 += JAC_TILE) {
+        const int cnt = (l_end - l0 < JAC_TILE) ? (int)(l_end - l0) : JAC_TILE;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < cnt; idx += JAC_THREADS) {
+            pts[0][idx] = a.j.xp[l0 + idx];
+            pts[1][idx] = a.j.yp[l0 + idx];
+            pts[2][idx] = a.j.zp[l0 + idx];
+            pts[3][idx] = a.weights[l0 + idx];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int r = 0; r < cnt; ++r) {
+            const double d = pts[3][r];
+            // the field is linear in the property: weight it before the evaluation
+            Eval::template pair<MASK>(acc, pts[0][r], pts[1][r], pts[2][r], x1, x2, y1, y2, z1, z2,
+                                      u0 * d, u1 * d, u2 * d, f);
+        }
+    }
+    if (active) a.part[(int64_t)blockIdx.y * a.ld_p + q] = acc[0];
+}
+
+template <uint32_t MASK, class Eval>
+inline cudaError_t launch_adjoint_t(const AdjointArgs &a, int nsplit, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((a.j.model.m + JAC_THREADS - 1) / JAC_THREADS), (unsigned)nsplit);
+    adjoint_kernel<MASK, Eval><<<grid, JAC_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <uint32_t MASK, class Eval>
 inline cudaError_t launch_jacobian_t(const JacobianArgs &a, bool transposed, cudaStream_t stream)
 {

@@ -14,4 +14,7 @@ cudaError_t launch_forward_fast_mag(uint32_t mask, const ForwardArgs &a, cudaStr
 cudaError_t launch_jacobian_exact(int field, bool transposed, const JacobianArgs &a, cudaStream_t s);  // jac_exact.cu
 cudaError_t launch_jacobian_fast(int field, bool transposed, const JacobianArgs &a, cudaStream_t s);   // jac_fast.cu
 
+cudaError_t launch_adjoint_exact(int field, const AdjointArgs &a, int nsplit, cudaStream_t s);   // jac_exact.cu
+cudaError_t launch_adjoint_fast(int field, const AdjointArgs &a, int nsplit, cudaStream_t s);    // jac_fast.cu
+
 }  // namespace fb200

@@ -30,6 +30,7 @@ the reference does not have, built on the same kernels:
 
 * :func:`fields` -- several components in one pass (shares the per-corner work);
 * :func:`jacobian` -- the dense sensitivity matrix, one column per cell;
+* :func:`adjoint` -- ``J.T @ data`` on the fly, without storing ``J``;
 * :class:`Model` -- upload a model once, evaluate many times.
 
 There is no CPU implementation in this package: without the CUDA library or a
@@ -216,6 +217,35 @@ class Model(object):
                 out.ctypes.data, shape[1], flags))
         return out
 
+    def adjoint(self, xp, yp, zp, data, field='gz', pmag=None, fvec=None,
+                reference_order=False, scaled=True):
+        """
+        ``J.T @ data`` without building ``J``: for every prism q, the sum over
+        the points of ``data[l]`` times the unit-property effect of q at l
+        (what ``imaging.migrate`` computes layer by layer, imaging.py:116-118).
+        Returns a float64 array with one entry per prism of the model.
+        """
+        xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
+        data = _as_points(data)
+        _check_points(xp, yp, zp, 'shape')
+        if data.shape != xp.shape:
+            raise ValueError("data must have one value per computation point")
+        fid = _lib.FIELD_ID[field]
+        out = numpy.zeros(self.size, dtype=numpy.float64)
+        if self.size:
+            if field in MAGNETIC_FIELDS:
+                if pmag is None:
+                    raise ValueError("magnetic adjoints need the unit magnetization pmag")
+                unit = numpy.ascontiguousarray(pmag, dtype=numpy.float64)
+            else:
+                unit = numpy.array([1.0])
+            fvec_arr = None if fvec is None else numpy.ascontiguousarray(fvec, dtype=numpy.float64)
+            _lib.check(_lib.lib().fb200_adjoint(
+                self._handle, xp.ctypes.data, yp.ctypes.data, zp.ctypes.data, xp.size, fid,
+                _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
+                data.ctypes.data, out.ctypes.data, self._flags(xp, yp, zp, reference_order)))
+        return out
+
     def last_kernel_ms(self):
         """(device milliseconds, kernel launches) of the last evaluation."""
         ms, launches = ctypes.c_double(0), ctypes.c_int(0)
@@ -318,6 +348,36 @@ def jacobian(xp, yp, zp, prisms, field='gz', inc=None, dec=None, pmag=None,
     else:
         full = numpy.zeros((xp.size, flat.total))
         full[:, flat.index] = jac
+    return full
+
+
+def adjoint(xp, yp, zp, prisms, data, field='gz', inc=None, dec=None, pmag=None, device=0, **kw):
+    """
+    Transposed sensitivity applied to a data vector, ``jacobian(...).T @ data``,
+    computed on the fly (nothing of size npoints x ncells is stored).
+
+    The reference builds this product layer by layer in ``imaging.migrate``
+    (``dot(sensibility_T, gz)``, imaging.py:116-118) and it is the gradient
+    product of a linear misfit (misfit.py:280-294).  One value per entry of
+    ``prisms``; masked cells (``None``) get 0.  Arguments as :func:`jacobian`.
+    """
+    _check_points(xp, yp, zp, 'shape')
+    fvec = None if inc is None else utils.dircos(inc, dec)
+    if field in MAGNETIC_FIELDS:
+        if field == 'tf' and fvec is None:
+            raise ValueError("'tf' needs the inducing field direction inc, dec")
+        if pmag is None:
+            if fvec is None:
+                raise ValueError("magnetic adjoints need pmag or inc, dec")
+            pmag = fvec
+        pmag = _pmag_vector(pmag, fvec)
+    flat = flatten(prisms, None, override=True)
+    with Model(flat, None, device=device) as model:
+        got = model.adjoint(xp, yp, zp, data, field, pmag=pmag, fvec=fvec, **kw)
+    if flat.size == flat.total:
+        return got
+    full = numpy.zeros(flat.total)
+    full[flat.index] = got
     return full
 
 

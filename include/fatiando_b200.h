@@ -128,6 +128,18 @@ int fb200_jacobian(fb200_model *model,
                    const double *fvec, double scale,
                    double *out, int64_t ld, uint32_t flags);
 
+/* ---- adjoint of the sensitivity: out[q] = scale * sum_l data[l] * J[l][q] --
+ * J^T d without storing J: what imaging.py:116-118 computes layer by layer as
+ * dot(array([prism.gz(x, y, z, [p], dens=1) for p in layer]), gz), and the
+ * gradient product of misfit.py:280-294.  Arguments as fb200_jacobian; data
+ * has n entries, out has m.  Partial sums over fixed contiguous ranges of the
+ * points are added in range order (reproducible run to run).                */
+int fb200_adjoint(fb200_model *model,
+                  const double *xp, const double *yp, const double *zp,
+                  int64_t n, int field, const double *unit_prop,
+                  const double *fvec, double scale,
+                  const double *data, double *out, uint32_t flags);
+
 /* ---- the reference's own FFI shape: one prism accumulated into res ------
  * `_prism.<field>(xp, yp, zp, x1, x2, y1, y2, z1, z2, <props>, res)` adds ONE
  * prism's effect into caller-owned res[0..n) and never zeroes it
