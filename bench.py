@@ -56,6 +56,10 @@ WORK = {
 # smsp__inst_executed_pipe_fp64 / pairs, see profiles/); None until measured.
 # c4: the Jacobian kernel runs the same pair evaluator as c5; the profiled first row block
 # executes 373 because 2/3 of its rows lie on mesh planes (careful variant), see profiles/.
+# DRAM traffic of the dominant kernel per launch (ncu dram__bytes_read.sum +
+# dram__bytes_write.sum, profiles/r01_*): the model and the points are read once, the
+# outputs (<= 2 MB) stay in L2 until the D2H copy.  Bytes per launch at the profiled size.
+DRAM_TRAFFIC_PER_LAUNCH = {"c2": 3.9e6, "c2a": 3.9e6, "c3": None, "c4": None, "c5": None, "c5t": None}
 EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3}   # profiles/r01_*
 
 
@@ -95,7 +99,7 @@ def make_workload(name, world=1):
         mesh.addprop('magnetization', mag)
         xp, yp, zp = gridder.regular((0, 10000, 0, 10000), (500 * world, 500), z=-300)
         return dict(model=mesh, prop='magnetization', names=['tf', 'bx', 'by', 'bz'],
-                    xp=xp, yp=yp, zp=zp, fvec=utils.dircos(inc, dec), kind='forward',
+                    xp=xp, yp=yp, zp=zp, fvec=utils.dircos(inc, dec), inc=inc, dec=dec, kind='forward',
                     label="C3: tf+bx+by+bz of PrismMesh 100x100x10 (1e5 prisms, induced+remanent) "
                           "on a %dx500 grid at z=-300" % (500 * world))
     if name == "c4":
@@ -214,7 +218,7 @@ def cpu_baseline(w, flat, seconds=15.0, cores=None):
     else:
         props = np.ones((m, 1))
     bounds = flat.bounds
-    per_field_rate = 2.5e6       # pairs/s/core, order of magnitude
+    per_field_rate = 1.5e6       # pairs/s/core per field call, sizing only
     pts_per_core = max(1, int(per_field_rate * seconds / (m * len(w['names']))))
     n_s = min(w['xp'].size, pts_per_core * cores)
     idx = np.linspace(0, w['xp'].size - 1, n_s).astype(np.int64)
@@ -345,12 +349,10 @@ def run_gpu(args):
     def step_e2e():
         if w['kind'] == 'jacobian':
             rows = min(n, 2048)      # host-resident J is PCIe-bound: bounded row block
-            j = prism.jacobian(xp[:rows], yp[:rows], zp[:rows], w['model'], names[0])
+            j = prism.jacobian(xp[:rows], yp[:rows], zp[:rows], w['model'], names[0], device=dev)
             return rows, j.nbytes
-        if w['prop'] == 'magnetization':
-            res = prism._magnetic(names, xp, yp, zp, w['model'], None, w['fvec'], 'shape', device=dev)
-        else:
-            res = prism._gravity(names, xp, yp, zp, w['model'], None, 'shape', device=dev)
+        res = prism.fields(xp, yp, zp, w['model'], names, inc=w.get('inc'), dec=w.get('dec'),
+                           device=dev)
         return n, sum(v.nbytes for v in res.values())
     step_e2e()
     barrier()
@@ -384,7 +386,8 @@ def run_gpu(args):
         executed = EXECUTED_FP64_PER_PAIR.get(args.workload)
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak if peak else None, "traffic": None,
+                    "frac": achieved / peak if peak else None,
+                    "traffic": DRAM_TRAFFIC_PER_LAUNCH.get(args.workload),
                     "peak_source": "DFMA-chain microbenchmark in this run (fb200_fp64_peak: burst %.2f, "
                                    "sustained %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 figure"
                                    % (burst.value, sustained.value),

@@ -75,15 +75,60 @@ struct fb200_model {
     std::mutex lock;   // one call at a time per handle
 };
 
-static int grow(double **buf, size_t *cap, size_t need)
+// Device memory comes from the stream-ordered allocator (cudaMallocAsync): its
+// pool keeps freed blocks cached (release threshold raised in resources_for),
+// so a one-shot call -- create model, evaluate, destroy -- pays microseconds,
+// not a synchronising cudaMalloc/cudaFree pair per array.
+static int grow(double **buf, size_t *cap, size_t need, cudaStream_t s)
 {
     if (need <= *cap) return FB200_OK;
-    if (*buf) cudaFree(*buf);
+    if (*buf) cudaFreeAsync(*buf, s);
     *buf = nullptr;
     *cap = 0;
-    CK(cudaMalloc((void **)buf, need * sizeof(double)));
+    CK(cudaMallocAsync((void **)buf, need * sizeof(double), s));
     *cap = need;
     return FB200_OK;
+}
+
+// Streams and timing events are pooled per device: creating them costs more
+// than evaluating the cookbook-sized models.
+struct StreamSet {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+static std::mutex g_pool_lock;
+static std::vector<StreamSet> g_pool[64];
+static bool g_pool_configured[64] = {false};
+
+static int acquire_streams(int device, StreamSet *out)
+{
+    {
+        std::lock_guard<std::mutex> hold(g_pool_lock);
+        if (!g_pool_configured[device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            g_pool_configured[device] = true;
+        }
+        if (!g_pool[device].empty()) {
+            *out = g_pool[device].back();
+            g_pool[device].pop_back();
+            return FB200_OK;
+        }
+    }
+    CK(cudaStreamCreateWithFlags(&out->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&out->ev0));
+    CK(cudaEventCreate(&out->ev1));
+    return FB200_OK;
+}
+
+static void release_streams(int device, const StreamSet &set)
+{
+    if (!set.stream) return;
+    std::lock_guard<std::mutex> hold(g_pool_lock);
+    g_pool[device].push_back(set);
 }
 
 // ---------------------------------------------------------------------------
@@ -204,7 +249,7 @@ extern "C" int fb200_device_info(int device, char *name, int name_len, int *sm_c
 // ---------------------------------------------------------------------------
 static int upload(double **dst, const double *src, int64_t m, int64_t m_pad, cudaStream_t s)
 {
-    CK(cudaMalloc((void **)dst, (size_t)m_pad * sizeof(double)));
+    CK(cudaMallocAsync((void **)dst, (size_t)m_pad * sizeof(double), s));
     CK(cudaMemsetAsync(*dst, 0, (size_t)m_pad * sizeof(double), s));
     if (m > 0) CK(cudaMemcpyAsync(*dst, src, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, s));
     return FB200_OK;
@@ -214,15 +259,16 @@ extern "C" int fb200_model_destroy(fb200_model *model)
 {
     if (!model) return FB200_OK;
     DeviceGuard g(model->device);
-    for (double *p : model->d_b) if (p) cudaFree(p);
-    if (model->d_dens) cudaFree(model->d_dens);
-    for (double *p : model->d_mag) if (p) cudaFree(p);
-    if (model->d_pts) cudaFree(model->d_pts);
-    if (model->d_out) cudaFree(model->d_out);
-    if (model->d_part) cudaFree(model->d_part);
-    if (model->ev0) cudaEventDestroy(model->ev0);
-    if (model->ev1) cudaEventDestroy(model->ev1);
-    if (model->stream) cudaStreamDestroy(model->stream);
+    cudaStream_t st = model->stream;
+    for (double *p : model->d_b) if (p) cudaFreeAsync(p, st);
+    if (model->d_dens) cudaFreeAsync(model->d_dens, st);
+    for (double *p : model->d_mag) if (p) cudaFreeAsync(p, st);
+    if (model->d_pts) cudaFreeAsync(model->d_pts, st);
+    if (model->d_out) cudaFreeAsync(model->d_out, st);
+    if (model->d_part) cudaFreeAsync(model->d_part, st);
+    StreamSet set;
+    set.stream = model->stream; set.ev0 = model->ev0; set.ev1 = model->ev1;
+    release_streams(model->device, set);
     delete model;
     return FB200_OK;
 }
@@ -266,9 +312,11 @@ extern "C" int fb200_model_create(int device, int64_t m, const double *x1, const
     auto cuda_rc = [](cudaError_t e, const char *what) {
         return e == cudaSuccess ? FB200_OK : fail(FB200_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
     };
-    CKM(cuda_rc(cudaStreamCreateWithFlags(&mod->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
-    CKM(cuda_rc(cudaEventCreate(&mod->ev0), "cudaEventCreate"));
-    CKM(cuda_rc(cudaEventCreate(&mod->ev1), "cudaEventCreate"));
+    {
+        StreamSet set;
+        CKM(acquire_streams(device, &set));
+        mod->stream = set.stream; mod->ev0 = set.ev0; mod->ev1 = set.ev1;
+    }
     for (int r = 0; r < 6; ++r) {
         CKM(upload(&mod->d_b[r], src[r], m, m_pad, mod->stream));
         canonical_zero_kernel<<<(unsigned)((m_pad + 255) / 256), 256, 0, mod->stream>>>(mod->d_b[r], m_pad);
@@ -387,7 +435,7 @@ static int run_set(fb200_model *mod, uint32_t set, uint32_t request, bool exact,
         return FB200_OK;
     }
     const int64_t ld_p = (n + 31) / 32 * 32;
-    int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * nc * ld_p);
+    int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * nc * ld_p, mod->stream);
     if (rc != FB200_OK) return rc;
     a.out = mod->d_part;
     a.ld = ld_p;
@@ -441,9 +489,9 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
     int64_t ld = ld_out;
     if (!on_device) {
         const int64_t np = (n + 31) / 32 * 32;
-        int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3);
+        int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3, mod->stream);
         if (rc != FB200_OK) return rc;
-        rc = grow(&mod->d_out, &mod->out_cap, (size_t)np * nreq);
+        rc = grow(&mod->d_out, &mod->out_cap, (size_t)np * nreq, mod->stream);
         if (rc != FB200_OK) return rc;
         CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
         CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
@@ -565,14 +613,14 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     }
     // host output: stream the matrix back in row blocks of <= 256 MiB
     const int64_t np = (n + 31) / 32 * 32;
-    int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3);
+    int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3, mod->stream);
     if (rc != FB200_OK) return rc;
     CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     CK(cudaMemcpyAsync(mod->d_pts + 2 * np, zp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     int64_t rows = std::max<int64_t>(JAC_TILE, ((int64_t)(256ll << 20) / 8 / m) / JAC_TILE * JAC_TILE);
     rows = std::min(rows, std::min(max_rows_grid, (n + JAC_TILE - 1) / JAC_TILE * JAC_TILE));
-    rc = grow(&mod->d_out, &mod->out_cap, (size_t)rows * m);
+    rc = grow(&mod->d_out, &mod->out_cap, (size_t)rows * m, mod->stream);
     if (rc != FB200_OK) return rc;
     double total_ms = 0.0;
     for (int64_t r0 = 0; r0 < n; r0 += rows) {
@@ -633,9 +681,9 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
     const int64_t mp = (m + 31) / 32 * 32;
     if (!on_device) {
         const int64_t np = (n + 31) / 32 * 32;
-        int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 4 + 32);
+        int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 4 + 32, mod->stream);
         if (rc != FB200_OK) return rc;
-        rc = grow(&mod->d_out, &mod->out_cap, (size_t)mp);
+        rc = grow(&mod->d_out, &mod->out_cap, (size_t)mp, mod->stream);
         if (rc != FB200_OK) return rc;
         if (n > 0) {
             CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
@@ -658,7 +706,7 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         nsplit = std::min<int64_t>(nsplit, 65535);
         const int64_t rows = ((tiles + nsplit - 1) / nsplit) * JAC_TILE;
         nsplit = (n + rows - 1) / rows;
-        int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * mp);
+        int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * mp, mod->stream);
         if (rc != FB200_OK) return rc;
         AdjointArgs a;
         std::memset(&a, 0, sizeof(a));
