@@ -51,6 +51,8 @@ WORK = {
     "c4": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
     "c5": dict(flop=1478.0, slots=1022.0, what="gz"),
     "c5t": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
+    "c5full": dict(flop=1478.0, slots=1022.0, what="gz"),
+    "c5tfull": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
 }
 # FP64-pipe instructions the fast kernels actually execute per pair (ncu
 # smsp__inst_executed_pipe_fp64 / pairs, see profiles/); None until measured.
@@ -60,7 +62,8 @@ WORK = {
 # dram__bytes_write.sum, profiles/r01_*): the model and the points are read once, the
 # outputs (<= 2 MB) stay in L2 until the D2H copy.  Bytes per launch at the profiled size.
 DRAM_TRAFFIC_PER_LAUNCH = {"c2": 3.9e6, "c2a": 3.9e6, "c3": None, "c4": None, "c5": None, "c5t": None}
-EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3}   # profiles/r01_*
+EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3,
+                          "c5full": 318.5, "c5tfull": 523.3}   # profiles/r01_*
 
 
 # --------------------------------------------------------------------------
@@ -112,6 +115,15 @@ def make_workload(name, world=1):
                     fvec=None, kind='jacobian',
                     label="C4: gz sensitivity matrix, %d rows (of 250000) x 40000 PrismMesh cells, "
                           "device-resident" % (rows * world))
+    if name in ("c5full", "c5tfull"):
+        # the north-star problem itself: ALL 1e6 points x 1e6 prisms, points sharded over
+        # the GPUs in use (strong scaling: the total work does not grow with N)
+        w = make_workload("c5" if name == "c5full" else "c5t", 1)
+        area = (0, 1e6, 0, 1e6)
+        w['xp'], w['yp'], w['zp'] = gridder.regular(area, (1000, 1000), z=-5000)
+        w['label'] = "C5 full: %s of a 1000x1000 PrismRelief (1e6 prisms) at all 1e6 points, z=-5000" % '+'.join(w['names'])
+        w['scaling'] = 'strong'
+        return w
     if name in ("c5", "c5t"):
         area, shape = (0, 1e6, 0, 1e6), (1000, 1000)
         x, y = gridder.regular(area, shape)
@@ -354,14 +366,17 @@ def run_gpu(args):
         res = prism.fields(xp, yp, zp, w['model'], names, inc=w.get('inc'), dec=w.get('dec'),
                            device=dev)
         return n, sum(v.nbytes for v in res.values())
-    step_e2e()
-    barrier()
-    t1 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        rows_done, d2h = step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t1) / e2e_steps
+    if args.no_e2e:
+        rows_done, d2h, e2e_s = n, 0, float('inf')
+    else:
+        step_e2e()
+        barrier()
+        t1 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            rows_done, d2h = step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - t1) / e2e_steps
     h2d = (6 + (3 if w['prop'] == 'magnetization' else (1 if w['prop'] else 0))) * m * 8 + 3 * rows_done * 8
 
     # ---- reduce over ranks: max time, summed work ----
@@ -412,8 +427,8 @@ def run_gpu(args):
             cpu.pop("seconds", None)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic (seeded numpy RandomState)",
+                "higher_is_better": True, "scaling": w.get('scaling', 'weak'), "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic (seeded numpy RandomState)",
                 "config": {"workload": w['label'], "pairs_per_step": pairs_step,
                            "fields": names, "parallelism": "obs-shard x%d" % world,
                            "l2": "flushed between steps (256 MiB memset); inputs (<4 MB) are "
@@ -439,8 +454,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORK))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (huge workloads)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200" and not args.workload.endswith("full"):
+        args.warmup = max(args.warmup, 3)       # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
     else:
