@@ -51,6 +51,7 @@ WORK = {
     "c4": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
     "c5": dict(flop=1478.0, slots=1022.0, what="gz"),
     "c5t": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
+    "c4full": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
     "c5full": dict(flop=1478.0, slots=1022.0, what="gz"),
     "c5tfull": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
 }
@@ -63,7 +64,7 @@ WORK = {
 # outputs (<= 2 MB) stay in L2 until the D2H copy.  Bytes per launch at the profiled size.
 DRAM_TRAFFIC_PER_LAUNCH = {"c2": 3.9e6, "c2a": 3.9e6, "c3": None, "c4": None, "c5": None, "c5t": None}
 EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3,
-                          "c5full": 318.5, "c5tfull": 523.3}   # profiles/r01_*
+                          "c5full": 318.5, "c5tfull": 523.3, "c4full": 318.5}   # profiles/r01_*
 
 
 # --------------------------------------------------------------------------
@@ -115,6 +116,15 @@ def make_workload(name, world=1):
                     fvec=None, kind='jacobian',
                     label="C4: gz sensitivity matrix, %d rows (of 250000) x 40000 PrismMesh cells, "
                           "device-resident" % (rows * world))
+    if name == "c4full":
+        # the whole 250000 x 40000 sensitivity matrix (80 GB) resident on ONE B200, or its
+        # row shards on several
+        w = make_workload("c4", 1)
+        xp, yp, zp = gridder.regular((0, 10000, 0, 10000), (500, 500), z=-100)
+        w['xp'], w['yp'], w['zp'] = xp, yp, zp
+        w['label'] = "C4 full: gz sensitivity matrix, 250000 observations x 40000 PrismMesh cells (80 GB fp64), device-resident, row-sharded over the GPUs in use"
+        w['scaling'] = 'strong'
+        return w
     if name in ("c5full", "c5tfull"):
         # the north-star problem itself: ALL 1e6 points x 1e6 prisms, points sharded over
         # the GPUs in use (strong scaling: the total work does not grow with N)
@@ -310,7 +320,10 @@ def run_gpu(args):
     m = flat.size
     names = w['names']
     ncomp = len(names)
-    model = prism.Model(flat, w['prop'], device=dev)
+    # hand the mesh object itself over, so that a regular PrismMesh also gets its
+    # node-sharing form (the per-cell arrays are uploaded either way)
+    model = prism.Model(w['model'], w['prop'], keep_all=w['prop'] is None, fvec=w['fvec'], device=dev,
+                        node_sharing=not args.per_cell)
     tdev = torch.device("cuda", dev)
     d_pts = [torch.from_numpy(a).to(tdev) for a in (xp, yp, zp)]
     ids = sorted(_lib.FIELD_ID[nm] for nm in names)
@@ -431,6 +444,8 @@ def run_gpu(args):
                 "dtype": "f64", "data": "synthetic (seeded numpy RandomState)",
                 "config": {"workload": w['label'], "pairs_per_step": pairs_step,
                            "fields": names, "parallelism": "obs-shard x%d" % world,
+                           "evaluation": ("node-sharing (regular mesh: one kernel evaluation per node)"
+                                          if model.nodes is not None else "per cell"),
                            "l2": "flushed between steps (256 MiB memset); inputs (<4 MB) are "
                                  "smem/L2-resident by design, kernel is FP64-bound"},
                 "wall_ms_per_step": 1e3 * wall_max / args.steps,
@@ -455,6 +470,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORK))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (huge workloads)")
+    ap.add_argument("--per-cell", action="store_true",
+                    help="evaluate regular meshes cell by cell (no node sharing)")
     args = ap.parse_args()
     if args.impl == "b200" and not args.workload.endswith("full"):
         args.warmup = max(args.warmup, 3)       # timing rule: at least 3 warm-up steps

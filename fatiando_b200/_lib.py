@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FB200_LIBRARY") or os.path.join(HERE, "libfatiando_b200.so")
 
 OK, EINVAL, ECUDA, EPROP, EUNSUP = 0, -1, -2, -3, -4
-DEVICE_POINTERS, REFERENCE_ORDER, TRANSPOSED, NO_PRISM_SPLIT = 1, 2, 4, 8
+DEVICE_POINTERS, REFERENCE_ORDER, TRANSPOSED, NO_PRISM_SPLIT, PER_CELL = 1, 2, 4, 8, 16
 
 FIELDS = ("potential", "gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz",
           "gzz", "tf", "bx", "by", "bz")
@@ -36,6 +36,8 @@ _SIGNATURES = {
                            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64)], ctypes.c_int),
     "fb200_model_create": ([ctypes.c_int, _i64] + [_dp] * 10 + [ctypes.POINTER(ctypes.c_void_p)],
                            ctypes.c_int),
+    "fb200_model_attach_mesh": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+                                + [_dp] * 8, ctypes.c_int),
     "fb200_model_destroy": ([ctypes.c_void_p], ctypes.c_int),
     "fb200_model_size": ([ctypes.c_void_p], _i64),
     "fb200_model_device": ([ctypes.c_void_p], ctypes.c_int),

@@ -19,6 +19,8 @@
 #include "prism_fastmath.cuh"
 #include "prism_launch.h"
 #include "prism_masks.h"
+#include "prism_forward.cuh"
+#include "prism_mesh.cuh"
 
 using namespace fb200;
 
@@ -70,6 +72,14 @@ struct fb200_model {
     double *d_pts = nullptr;  size_t pts_cap = 0;     // 3*n staged points
     double *d_out = nullptr;  size_t out_cap = 0;     // staged results
     double *d_part = nullptr; size_t part_cap = 0;    // prism-split partials
+    // optional node-sharing representation of a regular mesh (prism_mesh.cuh)
+    bool has_mesh = false;
+    int nxp = 0, nyp = 0, nzp = 0;
+    int64_t nnodes = 0;
+    double *d_nodes = nullptr;                          // xn | yn | zn
+    double *d_wdens = nullptr;                          // node weights of the density
+    double *d_wmag[3] = {nullptr, nullptr, nullptr};    // ... of mx, my, mz
+    double shift[3] = {0.0, 0.0, 0.0};
     double last_ms = 0.0;
     int last_launches = 0;
     std::mutex lock;   // one call at a time per handle
@@ -266,6 +276,9 @@ extern "C" int fb200_model_destroy(fb200_model *model)
     if (model->d_pts) cudaFreeAsync(model->d_pts, st);
     if (model->d_out) cudaFreeAsync(model->d_out, st);
     if (model->d_part) cudaFreeAsync(model->d_part, st);
+    if (model->d_nodes) cudaFreeAsync(model->d_nodes, st);
+    if (model->d_wdens) cudaFreeAsync(model->d_wdens, st);
+    for (double *p : model->d_wmag) if (p) cudaFreeAsync(p, st);
     StreamSet set;
     set.stream = model->stream; set.ev0 = model->ev0; set.ev1 = model->ev1;
     release_streams(model->device, set);
@@ -333,6 +346,43 @@ extern "C" int fb200_model_create(int device, int64_t m, const double *x1, const
     return FB200_OK;
 }
 
+extern "C" int fb200_model_attach_mesh(fb200_model *mod, int nx, int ny, int nz, const double *xn,
+                                       const double *yn, const double *zn,
+                                       const double *cell_size, const double *w_density,
+                                       const double *w_mx, const double *w_my, const double *w_mz)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    if (nx < 1 || ny < 1 || nz < 1) return fail(FB200_EINVAL, "mesh shape must be positive");
+    if (!xn || !yn || !zn || !cell_size) return fail(FB200_EINVAL, "NULL mesh array");
+    const int nmag = (w_mx != nullptr) + (w_my != nullptr) + (w_mz != nullptr);
+    if (nmag != 0 && nmag != 3) return fail(FB200_EINVAL, "w_mx, w_my, w_mz must be all NULL or all given");
+    if (!w_density && nmag == 0) return fail(FB200_EINVAL, "no node weights given");
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    if (mod->has_mesh) return fail(FB200_EINVAL, "a mesh is already attached to this model");
+    mod->nxp = nx + 1; mod->nyp = ny + 1; mod->nzp = nz + 1;
+    mod->nnodes = (int64_t)mod->nxp * mod->nyp * mod->nzp;
+    const int64_t n_pad = (mod->nnodes + TILE - 1) / TILE * TILE;
+    const int64_t ncoord = (int64_t)mod->nxp + mod->nyp + mod->nzp;
+    CK(cudaMallocAsync((void **)&mod->d_nodes, (size_t)ncoord * 8, mod->stream));
+    CK(cudaMemcpyAsync(mod->d_nodes, xn, (size_t)mod->nxp * 8, cudaMemcpyHostToDevice, mod->stream));
+    CK(cudaMemcpyAsync(mod->d_nodes + mod->nxp, yn, (size_t)mod->nyp * 8, cudaMemcpyHostToDevice, mod->stream));
+    CK(cudaMemcpyAsync(mod->d_nodes + mod->nxp + mod->nyp, zn, (size_t)mod->nzp * 8,
+                       cudaMemcpyHostToDevice, mod->stream));
+    canonical_zero_kernel<<<(unsigned)((ncoord + 255) / 256), 256, 0, mod->stream>>>(mod->d_nodes, ncoord);
+    int rc = FB200_OK;
+    if (w_density) rc = upload(&mod->d_wdens, w_density, mod->nnodes, n_pad, mod->stream);
+    const double *wm[3] = {w_mx, w_my, w_mz};
+    for (int r = 0; r < 3 && rc == FB200_OK && nmag == 3; ++r)
+        rc = upload(&mod->d_wmag[r], wm[r], mod->nnodes, n_pad, mod->stream);
+    if (rc != FB200_OK) return rc;
+    for (int r = 0; r < 3; ++r) mod->shift[r] = 0.00001 * cell_size[r];   // _prism.pyx:328-329
+    CK(cudaStreamSynchronize(mod->stream));
+    mod->has_mesh = true;
+    return FB200_OK;
+}
+
 extern "C" int64_t fb200_model_size(const fb200_model *model) { return model ? model->m : -1; }
 extern "C" int fb200_model_device(const fb200_model *model) { return model ? model->device : -1; }
 
@@ -383,6 +433,77 @@ static void view_of(const fb200_model *mod, bool magnetic, ModelView *v)
         v->p[1] = v->p[2] = nullptr;
     }
     v->m = mod->m;
+}
+
+static int reduce_split(fb200_model *mod, int nc, int64_t nsplit, int64_t n, int64_t ld_p,
+                        const double *scale, const int *out_row, double *d_out, int64_t ld_out)
+{
+    ReduceArgs r;
+    std::memset(&r, 0, sizeof(r));
+    r.part = mod->d_part; r.out = d_out; r.n = n; r.ld = ld_p; r.ld_out = ld_out;
+    r.nc = nc; r.nsplit = (int)nsplit;
+    for (int k = 0; k < nc; ++k) { r.scale[k] = scale[k]; r.out_row[k] = out_row[k]; }
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
+    reduce_partials_kernel<<<grid, 256, 0, mod->stream>>>(r);
+    CK(cudaGetLastError());
+    return FB200_OK;
+}
+
+// Node-sharing evaluation of one component set (regular mesh attached, no override).
+static int run_set_mesh(fb200_model *mod, uint32_t set, uint32_t request, bool allow_split,
+                        const double *d_xp, const double *d_yp, const double *d_zp, int64_t n,
+                        const double *fvec, const double *scale, double *d_out, int64_t ld_out)
+{
+    const bool magnetic = (set & MAGNETIC_MASK) != 0;
+    MeshArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.mesh.xn = mod->d_nodes;
+    a.mesh.yn = mod->d_nodes + mod->nxp;
+    a.mesh.zn = mod->d_nodes + mod->nxp + mod->nyp;
+    a.mesh.nxp = mod->nxp; a.mesh.nyp = mod->nyp; a.mesh.nzp = mod->nzp;
+    a.mesh.nnodes = mod->nnodes;
+    if (magnetic) for (int r = 0; r < 3; ++r) a.mesh.w[r] = mod->d_wmag[r];
+    else a.mesh.w[0] = mod->d_wdens;
+    for (int r = 0; r < 3; ++r) { a.mesh.sh[r] = mod->shift[r]; a.fvec[r] = fvec ? fvec[r] : 0.0; }
+    a.xp = d_xp; a.yp = d_yp; a.zp = d_zp; a.n = n;
+    const int nc = popc(set);
+    int c = 0;
+    for (int f = 0; f < F_COUNT; ++f) {
+        if (!(set & bit(f))) continue;
+        const int row = popc(request & (bit(f) - 1));
+        a.out_row[c] = row;
+        a.scale[c] = scale ? scale[row] : 1.0;
+        ++c;
+    }
+    const int64_t blocks_x = (n + FWD_THREADS - 1) / FWD_THREADS;
+    const int64_t tiles = (mod->nnodes + TILE - 1) / TILE;
+    int64_t nsplit = 1;
+    if (allow_split) {
+        const int64_t target = (int64_t)mod->sm_count * 20;
+        nsplit = std::min<int64_t>(std::max<int64_t>(1, (target + blocks_x - 1) / blocks_x), tiles);
+        nsplit = std::min<int64_t>(nsplit, 65535);
+    }
+    const int64_t chunk = ((tiles + nsplit - 1) / nsplit) * TILE;
+    nsplit = (mod->nnodes + chunk - 1) / chunk;
+    a.chunk = chunk;
+    a.nsplit = (int)nsplit;
+    if (nsplit == 1) {
+        a.out = d_out;
+        a.ld = ld_out;
+        CK(launch_mesh_forward(set, a, mod->stream));
+        mod->last_launches += 1;
+        return FB200_OK;
+    }
+    const int64_t ld_p = (n + 31) / 32 * 32;
+    int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * nc * ld_p, mod->stream);
+    if (rc != FB200_OK) return rc;
+    a.out = mod->d_part;
+    a.ld = ld_p;
+    CK(launch_mesh_forward(set, a, mod->stream));
+    rc = reduce_split(mod, nc, nsplit, n, ld_p, a.scale, a.out_row, d_out, ld_out);
+    if (rc != FB200_OK) return rc;
+    mod->last_launches += 2;
+    return FB200_OK;
 }
 
 // One instantiated component set over all points; handles the prism split.
@@ -440,14 +561,8 @@ static int run_set(fb200_model *mod, uint32_t set, uint32_t request, bool exact,
     a.out = mod->d_part;
     a.ld = ld_p;
     CK(launch(a));
-    ReduceArgs r;
-    std::memset(&r, 0, sizeof(r));
-    r.part = mod->d_part; r.out = d_out; r.n = n; r.ld = ld_p; r.ld_out = ld_out;
-    r.nc = nc; r.nsplit = (int)nsplit;
-    for (int k = 0; k < nc; ++k) { r.scale[k] = a.scale[k]; r.out_row[k] = a.out_row[k]; }
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
-    reduce_partials_kernel<<<grid, 256, 0, mod->stream>>>(r);
-    CK(cudaGetLastError());
+    rc = reduce_split(mod, nc, nsplit, n, ld_p, a.scale, a.out_row, d_out, ld_out);
+    if (rc != FB200_OK) return rc;
     mod->last_launches += 2;
     return FB200_OK;
 }
@@ -463,12 +578,12 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         return fail(FB200_EINVAL, "invalid field mask");
     if (n > 0 && (!xp || !yp || !zp || !out)) return fail(FB200_EINVAL, "NULL point or output array");
     if (ld_out < n) return fail(FB200_EINVAL, "ld_out smaller than n");
-    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_NO_PRISM_SPLIT))
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_NO_PRISM_SPLIT | FB200_PER_CELL))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_forward");
     const uint32_t gmask = field_mask & GRAVITY_MASK, mmask = field_mask & MAGNETIC_MASK;
-    if (gmask && !mod->d_dens && !dens_override)
+    if (gmask && !mod->d_dens && !dens_override && !(mod->has_mesh && mod->d_wdens))
         return fail(FB200_EPROP, "gravity field requested but the model holds no density");
-    if (mmask && !mod->d_mag[0] && !pmag_override)
+    if (mmask && !mod->d_mag[0] && !pmag_override && !(mod->has_mesh && mod->d_wmag[0]))
         return fail(FB200_EPROP, "magnetic field requested but the model holds no magnetization");
     if ((mmask & bit(F_TF)) && !fvec)
         return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
@@ -513,17 +628,26 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         }
     } else {
         CK(cudaEventRecord(mod->ev0, mod->stream));
+        // a regular mesh with node weights attached: node-sharing kernel, unless the
+        // caller overrides the property, wants the reference order or the per-cell path
+        const bool nodes_ok = mod->has_mesh && !exact && !init && !(flags & FB200_PER_CELL);
         if (gmask) {
+            const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
             for (uint32_t set : cover(gmask, kGravitySets)) {
-                int rc = run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
-                                 dens_override, fvec, scale, d_init, d_out, ld);
+                int rc = use_nodes
+                    ? run_set_mesh(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, fvec, scale, d_out, ld)
+                    : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
+                              dens_override, fvec, scale, d_init, d_out, ld);
                 if (rc != FB200_OK) return rc;
             }
         }
         if (mmask) {
+            const bool use_nodes = nodes_ok && mod->d_wmag[0] && !pmag_override;
             for (uint32_t set : cover(mmask, kMagneticSets)) {
-                int rc = run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
-                                 pmag_override, fvec, scale, d_init, d_out, ld);
+                int rc = use_nodes
+                    ? run_set_mesh(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, fvec, scale, d_out, ld)
+                    : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
+                              pmag_override, fvec, scale, d_init, d_out, ld);
                 if (rc != FB200_OK) return rc;
             }
         }

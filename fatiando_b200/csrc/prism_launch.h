@@ -4,6 +4,8 @@
 #include "prism_common.cuh"
 #include "prism_jacobian.cuh"
 
+namespace fb200 { struct MeshArgs; }
+
 namespace fb200 {
 
 // Each returns cudaErrorInvalidValue when `mask` is not one of the instantiated
@@ -16,5 +18,7 @@ cudaError_t launch_jacobian_fast(int field, bool transposed, const JacobianArgs 
 
 cudaError_t launch_adjoint_exact(int field, const AdjointArgs &a, int nsplit, cudaStream_t s);   // jac_exact.cu
 cudaError_t launch_adjoint_fast(int field, const AdjointArgs &a, int nsplit, cudaStream_t s);    // jac_fast.cu
+
+cudaError_t launch_mesh_forward(uint32_t mask, const MeshArgs &a, cudaStream_t s);               // fwd_mesh.cu
 
 }  // namespace fb200

@@ -1,0 +1,268 @@
+// prism_mesh.cuh -- node-sharing evaluation for REGULAR meshes (PrismMesh).
+//
+// In a regular mesh every interior node is a corner of eight cells.  The
+// reference evaluates it eight times, once per cell and with alternating sign
+// (fatiando/gravmag/_prism.pyx:88-104 inside the per-prism loop of
+// prism.py:131-141); summed over the mesh that is
+//
+//     field(P) = sum_nodes K(node - P) * W_node,
+//     W_node   = sum over the <= 8 adjacent cells of (+-) property
+//
+// with K the reference's per-corner kernel (_prism.pyx:36-68) and the sign that
+// of the corner the node is in that cell.  W is a 2x2x2 difference stencil of
+// the property field, built once on the host (fatiando_b200/flatten.py).  One
+// kernel evaluation per NODE instead of eight per CELL: per cell-equivalent the
+// six tensor components cost ~175 FP64 instructions instead of ~430, and nodes
+// whose weight is zero (uniform regions, masked cells) are skipped outright.
+//
+// The arithmetic per node is the reference's own: r = sqrt((dx*dx + dy*dy) +
+// dz*dz) with the same association and IEEE sqrt, safe_log / safe_atan2
+// semantics (log and atan evaluated by the fast-path primitives of
+// prism_fastmath.cuh), the 1e-5 shift of r for gxy/gxz/gyz.  What differs from
+// the per-cell path is (i) a shared node uses ONE coordinate where the
+// reference has x1 + dx of one cell and b0 + dx*(i+1) of the next (equal or one
+// ulp apart) and (ii) the order of the additions -- both far inside the parity
+// floor (tests: tests/test_hostsim.py, tests/test_gpu_parity.py).  The one place
+// where a one-ulp coordinate change matters is where the field itself is
+// discontinuous: observation points INSIDE the body exactly on the line through
+// mesh nodes (cell junctions).  There any two roundings disagree, the reference's
+// own cells with each other included; outside the body the direction-dependent
+// parts cancel along every node column (the weights of a column sum to zero).
+#pragma once
+#include "prism_common.cuh"
+#include "prism_fastmath.cuh"
+#include "prism_exact.cuh"
+
+namespace fb200 {
+
+// log(a) for a >= 0 with safe_log(0) = 0 (_prism.pyx:28-34)
+FB_HD double node_log(double a)
+{
+    const double arg = (a == 0.0) ? 1.0 : a;
+    return fm::log_ratio(arg, 1.0);
+}
+
+// safe_atan2(y, x) = atan(y / x) folded to [-pi/2, pi/2], 0 for y == 0 (_prism.pyx:16-26)
+FB_HD double node_atan(double y, double x)
+{
+    // (0, 0) -> 0: give the division a non-zero denominator
+    const double xs = (x == 0.0 && y == 0.0) ? 1.0 : x;
+    return fm::atan_ratio(y, xs);
+}
+
+// Contribution of one node to every requested component.
+//   X, Y, Z  : node - point;  XX_YY = X*X + Y*Y (hoisted per node column);
+//   w0..w2   : node weight (density stencil, or the three magnetization stencils);
+//   sh[3]    : 1e-5 * cell size in x, y, z (the singularity shift, _prism.pyx:327-330)
+template <uint32_t MASK>
+FB_HD void node_accumulate(double (&acc)[popc(MASK)], double X, double Y, double Z,
+                           double XX_YY, double w0, double w1, double w2,
+                           const double (&f)[3], const double (&sh)[3])
+{
+    using namespace fm;
+    const double ZZ = mul(Z, Z);
+    const double r2 = add(XX_YY, ZZ);
+    double r = root(r2);
+    // a node on (or within 2^-485 of) the point: outside the range of the
+    // branch-free root, take the library's
+    if (hi32(r2) < 0x03500000) r = sqrt(r2);
+    double Lx = 0, Ly = 0, Lz = 0, Axx = 0, Ayy = 0, Azz = 0;
+    if constexpr (MASK & NEED_LX) Lx = node_log(add(X, r));
+    if constexpr (MASK & NEED_LY) Ly = node_log(add(Y, r));
+    if constexpr (MASK & NEED_LZ) Lz = node_log(add(Z, r));
+    if constexpr (MASK & NEED_AXX) Axx = node_atan(mul(Z, Y), mul(X, r));
+    if constexpr (MASK & NEED_AYY) Ayy = node_atan(mul(Z, X), mul(Y, r));
+    if constexpr (MASK & NEED_AZZ) Azz = node_atan(mul(X, Y), mul(Z, r));
+    int c = 0;
+    if constexpr (MASK & bit(F_POT))     // _prism.pyx:36-39
+        acc[c++] += (X * Y * Lz + Y * Z * Lx + X * Z * Ly - 0.5 * (X * X) * Axx
+                     - 0.5 * (Y * Y) * Ayy - 0.5 * ZZ * Azz) * w0;
+    if constexpr (MASK & bit(F_GX)) acc[c++] += (X * Axx - (Y * Lz + Z * Ly)) * w0;   // :43-44
+    if constexpr (MASK & bit(F_GY)) acc[c++] += (Y * Ayy - (Z * Lx + X * Lz)) * w0;   // :46-47
+    if constexpr (MASK & bit(F_GZ)) acc[c++] += (Z * Azz - (X * Ly + Y * Lx)) * w0;   // :49-50
+    if constexpr (MASK & bit(F_GXX)) acc[c++] -= Axx * w0;                            // :52-53
+    if constexpr (MASK & bit(F_GXY)) {                                                // :55-56
+        double L = Lz;
+        if (X == 0.0 && Y == 0.0 && Z < 0.0)
+            L = safe_log_ref(add(Z, sqrt(add(add(mul(sh[0], sh[0]), mul(sh[1], sh[1])), ZZ))));
+        acc[c++] += L * w0;
+    }
+    if constexpr (MASK & bit(F_GXZ)) {                                                // :58-59
+        double L = Ly;
+        if (X == 0.0 && Z == 0.0 && Y < 0.0)
+            L = safe_log_ref(add(Y, sqrt(add(add(mul(sh[0], sh[0]), mul(sh[2], sh[2])), mul(Y, Y)))));
+        acc[c++] += L * w0;
+    }
+    if constexpr (MASK & bit(F_GYY)) acc[c++] -= Ayy * w0;                            // :61-62
+    if constexpr (MASK & bit(F_GYZ)) {                                                // :64-65
+        double L = Lx;
+        if (Y == 0.0 && Z == 0.0 && X < 0.0)
+            L = safe_log_ref(add(X, sqrt(add(add(mul(sh[1], sh[1]), mul(sh[2], sh[2])), mul(X, X)))));
+        acc[c++] += L * w0;
+    }
+    if constexpr (MASK & bit(F_GZZ)) acc[c++] -= Azz * w0;                            // :67-68
+    if constexpr (MASK & MAGNETIC_MASK) {
+        // v1..v6 of _prism.pyx:94-99 at this node; w0..w2 are the stencils of mx, my, mz
+        const double bx = fma(-Axx, w0, fma(Lz, w1, Ly * w2));
+        const double by = fma(Lz, w0, fma(-Ayy, w1, Lx * w2));
+        const double bz = fma(Ly, w0, fma(Lx, w1, -Azz * w2));
+        if constexpr (MASK & bit(F_TF)) acc[c++] += fma(f[0], bx, fma(f[1], by, f[2] * bz));
+        if constexpr (MASK & bit(F_BX)) acc[c++] += bx;
+        if constexpr (MASK & bit(F_BY)) acc[c++] += by;
+        if constexpr (MASK & bit(F_BZ)) acc[c++] += bz;
+    }
+}
+
+
+#if defined(__CUDACC__)
+// ---- the kernel ---------------------------------------------------------------
+// thread = observation point, as in prism_forward.cuh.  Nodes are walked with z
+// fastest, so X, Y and X*X + Y*Y are recomputed only once per node column; the
+// node weights (1 or 3 rows) come through the same two-stage TMA/mbarrier ring as
+// the prism tiles of the per-cell kernel; the node coordinate vectors (a few
+// hundred doubles) are read through L1 (x, y: once per column) or shared memory (z).
+struct MeshView {
+    const double *xn, *yn, *zn;   // node coordinates, nxp, nyp, nzp entries
+    int nxp, nyp, nzp;
+    const double *w[3];           // node weights, index (b*nxp + a)*nzp + c
+    int64_t nnodes;
+    double sh[3];                 // 1e-5 * cell size (singularity shift)
+};
+
+struct MeshArgs {
+    MeshView mesh;
+    const double *xp, *yp, *zp;
+    int64_t n;
+    double fvec[3];
+    int64_t chunk;                // nodes per blockIdx.y, multiple of TILE
+    int nsplit;
+    double *out;
+    int64_t ld;
+    double scale[F_COUNT];
+    int out_row[F_COUNT];
+};
+
+constexpr int MESH_ZMAX = 2048;   // z node levels kept in shared memory
+
+template <uint32_t MASK>
+__global__ void __launch_bounds__(FWD_THREADS, FB200_FWD_MIN_BLOCKS)
+mesh_forward_kernel(const MeshArgs a)
+{
+    constexpr int NC = popc(MASK);
+    constexpr bool MAG = (MASK & MAGNETIC_MASK) != 0;
+    constexpr int ROWS = MAG ? 3 : 1;
+    __shared__ __align__(128) double sp[FWD_STAGES][ROWS][TILE];
+    __shared__ __align__(8) uint64_t full_bar[FWD_STAGES];
+    __shared__ unsigned done_cnt[FWD_STAGES];
+    extern __shared__ double zn_s[];
+
+    const MeshView &mv = a.mesh;
+    int64_t l = (int64_t)blockIdx.x * FWD_THREADS + threadIdx.x;
+    const bool active = l < a.n;
+    if (!active) l = a.n - 1;
+    const double xp = a.xp[l], yp = a.yp[l], zp = a.zp[l];
+    const double f[3] = {a.fvec[0], a.fvec[1], a.fvec[2]};
+    const double sh[3] = {mv.sh[0], mv.sh[1], mv.sh[2]};
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+
+    const int64_t g0 = (int64_t)blockIdx.y * a.chunk;
+    const int64_t g1 = (g0 + a.chunk < mv.nnodes) ? g0 + a.chunk : mv.nnodes;
+    const int ntiles = (int)((g1 - g0 + TILE - 1) / TILE);
+    const bool z_in_smem = mv.nzp <= MESH_ZMAX;
+
+    auto issue = [&](int t, int s) {
+        const int64_t off = g0 + (int64_t)t * TILE;
+        mbar_expect_tx(&full_bar[s], (unsigned)(ROWS * TILE * sizeof(double)));
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            tma_load_1d(&sp[s][r][0], mv.w[r] + off, TILE * sizeof(double), &full_bar[s]);
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < FWD_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            done_cnt[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (z_in_smem)
+        for (int i = threadIdx.x; i < mv.nzp; i += FWD_THREADS) zn_s[i] = mv.zn[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FWD_STAGES && s < ntiles; ++s) issue(s, s);
+    }
+
+    // position of the first node of this chunk: column (a_, b_) and level c_
+    int64_t col = g0 / mv.nzp;
+    int c_ = (int)(g0 - col * mv.nzp);
+    int b_ = (int)(col / mv.nxp);
+    int a_ = (int)(col - (int64_t)b_ * mv.nxp);
+    double X = fm::sub(mv.xn[a_], xp), Y = fm::sub(mv.yn[b_ < mv.nyp ? b_ : mv.nyp - 1], yp);
+    double sxy = fm::add(fm::mul(X, X), fm::mul(Y, Y));
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % FWD_STAGES;
+        mbar_wait(&full_bar[s], (unsigned)((t / FWD_STAGES) & 1));
+        const int64_t base = g0 + (int64_t)t * TILE;
+        const int cnt = (g1 - base < TILE) ? (int)(g1 - base) : TILE;
+#pragma unroll 1
+        for (int q = 0; q < cnt; ++q) {
+            const double w0 = sp[s][0][q];
+            const double w1 = MAG ? sp[s][ROWS > 1 ? 1 : 0][q] : 0.0;
+            const double w2 = MAG ? sp[s][ROWS > 2 ? 2 : 0][q] : 0.0;
+            // zero weight (uniform region, masked cells): nothing to add -- uniform branch
+            const bool live = MAG ? (w0 != 0.0 || w1 != 0.0 || w2 != 0.0) : (w0 != 0.0);
+            if (live) {
+                const double Z = fm::sub(z_in_smem ? zn_s[c_] : mv.zn[c_], zp);
+                node_accumulate<MASK>(acc, X, Y, Z, sxy, w0, w1, w2, f, sh);
+            }
+            if (++c_ == mv.nzp) {      // next node column: new X (and Y at the end of a row)
+                c_ = 0;
+                if (++a_ == mv.nxp) {
+                    a_ = 0;
+                    ++b_;
+                    if (b_ < mv.nyp) Y = fm::sub(mv.yn[b_], yp);
+                }
+                X = fm::sub(mv.xn[a_], xp);
+                sxy = fm::add(fm::mul(X, X), fm::mul(Y, Y));
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            __threadfence_block();
+            const unsigned before = atomicAdd(&done_cnt[s], 1u);
+            if (before == FWD_WARPS - 1) {
+                done_cnt[s] = 0;
+                if (t + FWD_STAGES < ntiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(t + FWD_STAGES, s);
+                }
+            }
+        }
+    }
+    if (!active) return;
+    if (a.nsplit == 1) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            a.out[(int64_t)a.out_row[c] * a.ld + l] = acc[c] * a.scale[c];
+    } else {
+        double *part = a.out + (int64_t)blockIdx.y * NC * a.ld;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) part[(int64_t)c * a.ld + l] = acc[c];
+    }
+}
+
+template <uint32_t MASK>
+inline cudaError_t launch_mesh_t(const MeshArgs &a, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((a.n + FWD_THREADS - 1) / FWD_THREADS), (unsigned)a.nsplit);
+    const size_t zbytes = a.mesh.nzp <= MESH_ZMAX ? (size_t)a.mesh.nzp * sizeof(double) : 0;
+    mesh_forward_kernel<MASK><<<grid, FWD_THREADS, zbytes, stream>>>(a);
+    return cudaGetLastError();
+}
+#endif  // __CUDACC__
+
+}  // namespace fb200

@@ -31,15 +31,18 @@ class FlatModel(object):
     * magnetization : float64 array (m, 3) or None
     * index : int64 array (m,), position of each kept prism in the input
     * total : number of entries of the input (kept + dropped)
+    * nodes : :class:`MeshNodes` when the input was a regular ``PrismMesh``
+      carrying the property (its node-sharing form), else ``None``
     """
 
-    def __init__(self, bounds, density, magnetization, index, total):
+    def __init__(self, bounds, density, magnetization, index, total, nodes=None):
         self.bounds = [np.ascontiguousarray(b, dtype=np.float64) for b in bounds]
         self.density = None if density is None else np.ascontiguousarray(density, dtype=np.float64)
         self.magnetization = (None if magnetization is None
                               else np.ascontiguousarray(magnetization, dtype=np.float64))
         self.index = np.ascontiguousarray(index, dtype=np.int64)
         self.total = int(total)
+        self.nodes = nodes
 
     @property
     def size(self):
@@ -116,6 +119,83 @@ def _property_arrays(props, size):
     return dens, mag, False
 
 
+class MeshNodes(object):
+    """
+    Node-sharing form of a regular ``PrismMesh`` (see csrc/prism_mesh.cuh).
+
+    * xn, yn, zn : node coordinates (nx+1, ny+1, nz+1), the reference's own bound
+      expressions: ``b0 + d*i`` for i < n and ``(b0 + d*(n-1)) + d`` for the last
+      (mesh.py:629-634)
+    * cell_size : (dx, dy, dz)
+    * weights : list of 1 (density) or 3 (mx, my, mz) float64 arrays of
+      ``(nx+1)*(ny+1)*(nz+1)`` node weights, z fastest.  The weight of a node is
+      the signed sum of the property of the (up to) eight cells it is a corner
+      of: ``+`` where it is the cell's (x2, y2, z2)-type corner, alternating with
+      every bound that is the lower one instead ((-1)**(i+j+k), _prism.pyx:104).
+      Masked cells count as zero.
+    """
+
+    def __init__(self, shape, xn, yn, zn, cell_size, weights):
+        self.shape = shape
+        self.xn, self.yn, self.zn = xn, yn, zn
+        self.cell_size = np.array(cell_size, dtype=np.float64)
+        self.weights = weights
+
+
+def _node_coordinates(b0, d, n):
+    i = np.arange(n, dtype=np.float64)
+    lower = float(b0) + float(d) * i
+    return np.concatenate([lower, [lower[-1] + float(d)]])
+
+
+def _node_weights(values, shape):
+    """2x2x2 signed-sum stencil of a per-cell property, returned z fastest."""
+    nz, ny, nx = shape
+    pad = np.zeros((nz + 2, ny + 2, nx + 2))
+    pad[1:-1, 1:-1, 1:-1] = values.reshape(nz, ny, nx)
+    w = np.zeros((nz + 1, ny + 1, nx + 1))
+    for dc in (0, 1):
+        for db in (0, 1):
+            for da in (0, 1):
+                sign = -1.0 if (da + db + dc) % 2 else 1.0
+                w += sign * pad[dc:dc + nz + 1, db:db + ny + 1, da:da + nx + 1]
+    return np.ascontiguousarray(np.transpose(w, (1, 2, 0))).ravel()     # [b][a][c]
+
+
+def mesh_nodes(mesh, prop, fvec=None):
+    """
+    :class:`MeshNodes` of a regular ``PrismMesh`` carrying ``prop`` on every
+    cell, or ``None`` when ``mesh`` is not such a mesh (then only the per-cell
+    evaluation applies).
+    """
+    if not _is_prism_mesh(mesh) or prop not in getattr(mesh, 'props', {}):
+        return None
+    nz, ny, nx = (int(v) for v in mesh.shape)
+    size = nx * ny * nz
+    dens, mag, generic = _property_arrays(mesh.props, size)
+    if generic:
+        return None
+    dx, dy, dz = (float(d) for d in mesh.dims)
+    if not (dx > 0 and dy > 0 and dz > 0):
+        return None
+    keep = np.ones(size)
+    mask = getattr(mesh, 'mask', None)
+    if mask is not None and len(mask):
+        keep[np.asarray(mask, dtype=np.int64)] = 0.0
+    if prop == 'density':
+        channels = [dens * keep]
+    else:
+        if mag.ndim == 1:
+            mag = _expand_scalar_magnetization(mag, fvec)
+        channels = [mag[:, c] * keep for c in range(3)]
+    if not all(np.all(np.isfinite(ch)) for ch in channels):
+        return None
+    b = mesh.bounds
+    return MeshNodes((nz, ny, nx), _node_coordinates(b[0], dx, nx), _node_coordinates(b[2], dy, ny),
+                     _node_coordinates(b[4], dz, nz), (dx, dy, dz),
+                     [_node_weights(ch, (nz, ny, nx)) for ch in channels])
+
+
 def flatten(prisms, prop=None, override=False, fvec=None):
     """
     Flatten ``prisms`` for a field that needs physical property ``prop``.
@@ -156,7 +236,10 @@ def flatten(prisms, prop=None, override=False, fvec=None):
         mag = None
     if mag is not None and mag.ndim == 1:
         mag = _expand_scalar_magnetization(mag, fvec)
-    return FlatModel(bounds, dens, mag, index, total)
+    nodes = None
+    if prop is not None and not override and index.size:
+        nodes = mesh_nodes(prisms, prop, fvec=fvec)
+    return FlatModel(bounds, dens, mag, index, total, nodes)
 
 
 def _expand_scalar_magnetization(values, fvec):

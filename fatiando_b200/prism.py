@@ -51,6 +51,10 @@ MAGNETIC_FIELDS = ('tf', 'bx', 'by', 'bz')
 # of the collapsed corner sums of the fast path would leave the double range).
 FAST_PATH_MAX_COORD = 1e15
 
+# Regular meshes are evaluated node by node (each mesh node once, instead of once
+# per adjacent cell) when this is True; set to False to force the per-cell kernels.
+NODE_SHARING = True
+
 
 def unit_scale(field):
     """The unit factor the reference multiplies each field by."""
@@ -101,10 +105,16 @@ class Model(object):
     * fvec : inducing-field direction, to expand scalar magnetizations
     * device : CUDA device index
 
+    * node_sharing : for a regular ``PrismMesh`` also upload the node-sharing
+      form (one kernel evaluation per mesh node instead of eight per cell,
+      csrc/prism_mesh.cuh); forward fields then use it unless an override or
+      ``per_cell=True`` is given.  Same tolerance as the per-cell path.
+
     Use as a context manager or call :meth:`close`.
     """
 
-    def __init__(self, prisms, prop='density', keep_all=False, fvec=None, device=0):
+    def __init__(self, prisms, prop='density', keep_all=False, fvec=None, device=0,
+                 node_sharing=True):
         flat = prisms if isinstance(prisms, FlatModel) else \
             flatten(prisms, prop, override=keep_all, fvec=fvec)
         self.flat = flat
@@ -120,6 +130,16 @@ class Model(object):
             device, flat.size, *[_lib.dptr(b) for b in flat.bounds],
             _lib.dptr(flat.density), *[_lib.dptr(c) for c in cols],
             ctypes.byref(self._handle)))
+        self.nodes = flat.nodes if (node_sharing and NODE_SHARING) else None
+        if self.nodes is not None:
+            nd = self.nodes
+            nz, ny, nx = nd.shape
+            w = nd.weights
+            wd = w[0] if prop == 'density' else None
+            wm = w if prop == 'magnetization' else [None, None, None]
+            _lib.check(lib.fb200_model_attach_mesh(
+                self._handle, nx, ny, nz, _lib.dptr(nd.xn), _lib.dptr(nd.yn), _lib.dptr(nd.zn),
+                _lib.dptr(nd.cell_size), _lib.dptr(wd), *[_lib.dptr(c) for c in wm]))
 
     # -- lifetime ----------------------------------------------------------
     def close(self):
@@ -147,7 +167,7 @@ class Model(object):
         return 0
 
     def fields(self, xp, yp, zp, names, dens=None, pmag=None, fvec=None,
-               reference_order=False, scaled=True, list_order=False):
+               reference_order=False, scaled=True, list_order=False, per_cell=False):
         """
         Evaluate several components in one pass.
 
@@ -157,6 +177,7 @@ class Model(object):
         ``list_order=True`` forbids splitting the prism list over thread blocks:
         every point then sums the prisms strictly in list order, so any
         observation shard of a run reproduces the same bits as the full run.
+        ``per_cell=True`` bypasses the node-sharing form of a regular mesh.
         """
         xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
         _check_points(xp, yp, zp, 'shape')
@@ -177,7 +198,8 @@ class Model(object):
                 _lib.dptr(dens_arr), _lib.dptr(pmag_arr), _lib.dptr(fvec_arr),
                 _lib.dptr(scale), out.ctypes.data, n,
                 self._flags(xp, yp, zp, reference_order)
-                | (_lib.NO_PRISM_SPLIT if list_order else 0)))
+                | (_lib.NO_PRISM_SPLIT if list_order else 0)
+                | (_lib.PER_CELL if per_cell else 0)))
         return {_lib.FIELDS[i]: out[c] for c, i in enumerate(ids)}
 
     def jacobian(self, xp, yp, zp, field='gz', pmag=None, fvec=None, transposed=False,

@@ -10,6 +10,7 @@
 #include <cstdint>
 #include "../../fatiando_b200/csrc/prism_masks.h"
 #include "../../fatiando_b200/csrc/prism_fast.cuh"
+#include "../../fatiando_b200/csrc/prism_mesh.cuh"
 
 using namespace fb200;
 
@@ -39,6 +40,50 @@ extern "C" int hostsim_forward(uint32_t mask, int exact, const double *xp, const
         if (exact) run<(M), EvalExact>(xp, yp, zp, n, m, bounds, props, fvec, out);     \
         else run<(M), EvalFast>(xp, yp, zp, n, m, bounds, props, fvec, out);            \
         return 0;                                                                       \
+    }
+    FB200_GRAVITY_SETS(CASE)
+    FB200_MAGNETIC_SETS(CASE)
+#undef CASE
+    return -1;
+}
+
+// node-sharing evaluation of a regular mesh, same walk as mesh_forward_kernel
+template <uint32_t MASK>
+static void run_mesh(const double *xp, const double *yp, const double *zp, size_t n, int nxp, int nyp,
+                     int nzp, const double *xn, const double *yn, const double *zn,
+                     const double *const *w, const double *shv, const double *f, double *out)
+{
+    constexpr int NC = popc(MASK);
+    constexpr bool MAG = (MASK & MAGNETIC_MASK) != 0;
+    const double fv[3] = {f[0], f[1], f[2]}, sh[3] = {shv[0], shv[1], shv[2]};
+    for (size_t l = 0; l < n; ++l) {
+        double acc[NC];
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+        size_t g = 0;
+        for (int b = 0; b < nyp; ++b)
+            for (int a = 0; a < nxp; ++a) {
+                const double X = xn[a] - xp[l], Y = yn[b] - yp[l];
+                const double sxy = X * X + Y * Y;
+                for (int c = 0; c < nzp; ++c, ++g) {
+                    const double w0 = w[0][g], w1 = MAG ? w[1][g] : 0.0, w2 = MAG ? w[2][g] : 0.0;
+                    if (w0 == 0.0 && w1 == 0.0 && w2 == 0.0) continue;
+                    node_accumulate<MASK>(acc, X, Y, zn[c] - zp[l], sxy, w0, w1, w2, fv, sh);
+                }
+            }
+        for (int c = 0; c < NC; ++c) out[(size_t)c * n + l] = acc[c];
+    }
+}
+
+extern "C" int hostsim_mesh_forward(uint32_t mask, const double *xp, const double *yp,
+                                    const double *zp, size_t n, int nxp, int nyp, int nzp,
+                                    const double *xn, const double *yn, const double *zn,
+                                    const double *const *w, const double *sh, const double *fvec,
+                                    double *out)
+{
+#define CASE(M)                                                                          \
+    if (mask == (M)) {                                                                   \
+        run_mesh<(M)>(xp, yp, zp, n, nxp, nyp, nzp, xn, yn, zn, w, sh, fvec, out);       \
+        return 0;                                                                        \
     }
     FB200_GRAVITY_SETS(CASE)
     FB200_MAGNETIC_SETS(CASE)

@@ -323,6 +323,46 @@ def test_size_independent_properties_at_scale(gpu_lib):
     np.testing.assert_allclose(t2, 2.0 * t['gzz'], rtol=1e-12, atol=1e-12 * scale)
 
 
+def test_node_sharing_equals_per_cell_and_oracle(gpu_lib, oracle):
+    """Regular meshes: the node-sharing kernel (default) against the per-cell kernel and
+    the oracle, with masked cells, grid lines in mesh planes and points inside the mesh."""
+    from fatiando_b200 import prism, mesher, gridder, utils
+    from fatiando_b200.flatten import flatten
+    rs = np.random.RandomState(21)
+    mesh = mesher.PrismMesh((0, 5000, -300, 4100, 10, 2000), (5, 9, 11))
+    mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+    mesh.addprop('magnetization', rs.uniform(-2, 2, (mesh.size, 3)))
+    mesh.mask = [0, 4, 17, 50, 104, 400]
+    grids = [gridder.regular((0, 5000, -300, 4100), (23, 19), z=-150),
+             # inside the body, on a node level in z, but off the vertical lines through mesh
+             # nodes: ON those lines inside the body the tensor is discontinuous and any two
+             # roundings of the coordinates disagree (the reference included)
+             gridder.regular((100, 4900, -200, 4000), (12, 10), z=408.0),
+             gridder.regular((-3e5, 3e5, -3e5, 3e5), (9, 7), z=-4e4)]
+    fv = utils.dircos(30, -15)
+    for xp, yp, zp in grids:
+        for prop, names in (('density', GRAV), ('magnetization', MAG)):
+            flat = flatten(mesh, prop)
+            props = flat.density[:, None] if prop == 'density' else flat.magnetization
+            with prism.Model(mesh, prop) as model:
+                assert model.nodes is not None
+                nodes = model.fields(xp, yp, zp, names, fvec=fv)
+                cells = model.fields(xp, yp, zp, names, fvec=fv, per_cell=True)
+            for f in names:
+                pr = props if f != 'tf' else np.hstack([props, np.tile(fv, (props.shape[0], 1))])
+                ref = oracle.model(f, xp, yp, zp, flat.bounds, pr)
+                cond = oracle.condition(f, xp, yp, zp, flat.bounds, pr)
+                assert_parity(nodes[f], ref, cond, C_FLOOR_FAST, 'node sharing ' + f)
+                assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'per cell ' + f)
+    # dens= override bypasses the node weights (they belong to the mesh's own densities)
+    xp, yp, zp = grids[0]
+    flat = flatten(mesh, 'density')
+    got = prism.gz(xp, yp, zp, mesh, dens=250.0)
+    ref = oracle.model('gz', xp, yp, zp, flat.bounds, np.full((flat.size, 1), 250.0))
+    cond = oracle.condition('gz', xp, yp, zp, flat.bounds, np.full((flat.size, 1), 250.0))
+    assert_parity(got, ref, cond, C_FLOOR_FAST, 'override on a mesh')
+
+
 def test_negative_zero_bounds_and_points_on_planes(gpu_lib, oracle):
     """-0.0 bounds (e.g. z = -1*0.0 from a flat relief) with points in those planes:
     the reference tests `x < 0`, false for -0.0; the kernel reads sign bits, so the

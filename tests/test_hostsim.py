@@ -159,3 +159,65 @@ def test_far_field_relief(hostsim, oracle):
     ref = oracle.model('gz', xp, yp, zp, b, dens, scale=1.0)
     cond = oracle.condition('gz', xp, yp, zp, b, dens, scale=1.0)
     assert np.max(np.abs(fast - ref) / (EPS * cond)) < 0.25
+
+
+def mesh_forward(H, mask, xp, yp, zp, nodes, f=(0, 0, 0)):
+    xp, yp, zp = (np.ascontiguousarray(a, dtype=float) for a in (xp, yp, zp))
+    out = np.zeros((bin(mask).count('1'), xp.size))
+    w = [np.ascontiguousarray(a) for a in nodes.weights]
+    warr = (dp * 3)(*([_p(a) for a in w] + [None] * (3 - len(w))))
+    sh = 0.00001 * nodes.cell_size
+    fv = np.array(f, dtype=float)
+    rc = H.hostsim_mesh_forward(ctypes.c_uint32(mask), _p(xp), _p(yp), _p(zp), ctypes.c_size_t(xp.size),
+                                nodes.xn.size, nodes.yn.size, nodes.zn.size, _p(nodes.xn),
+                                _p(nodes.yn), _p(nodes.zn), warr, _p(sh), _p(fv), _p(out))
+    assert rc == 0
+    return out
+
+
+def test_node_sharing_matches_the_per_cell_reference(hostsim, oracle):
+    """Regular meshes evaluated once per NODE (csrc/prism_mesh.cuh) against the oracle's
+    per-cell loop: plain and awkward bounds, masked cells, grids on the mesh planes,
+    points inside the mesh, far points; gravity sets and magnetic sets."""
+    from fatiando_b200 import mesher, gridder, utils
+    from fatiando_b200.flatten import flatten, mesh_nodes
+    rs = np.random.RandomState(12)
+    cases = [((4, 6, 7), (0, 5000, 0, 5000, 0, 2000), -150.0, None),
+             ((3, 7, 5), (0.1, 5000.3, -0.7, 4999.9, 0.05, 2000.95), -150.0, [0, 9, 40, 104]),
+             ((4, 6, 7), (0, 5000, 0, 5000, 0, 2000), -60000.0, [3, 50]),
+             ((2, 5, 5), (0, 500, 0, 500, 0, 200), 100.0, None),          # grid through the mesh
+             # seen from 60 body sizes away on every side: on the +x / +y side the reference
+             # folds atan2 by pi (oracle abs_atan_terms) and is itself the inaccurate one
+             ((3, 4, 5), (0, 5000, -300, 4100, 10, 2000), 'far', [7])]
+    for shape, bounds, z0, mask in cases:
+        mesh = mesher.PrismMesh(bounds, shape)
+        mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+        mesh.addprop('magnetization', rs.uniform(-2, 2, (mesh.size, 3)))
+        if mask:
+            mesh.mask = mask
+        nx, ny = shape[2], shape[1]
+        # every second grid line lies in a mesh plane
+        if z0 == 'far':
+            xp, yp, zp = gridder.regular((-3e5, 3e5, -3e5, 3e5), (9, 7), z=-4e4)
+        else:
+            xp, yp, zp = gridder.regular((bounds[0], bounds[1], bounds[2], bounds[3]),
+                                         (2 * nx + 1, 2 * ny + 1), z=z0)
+        for prop, sets, f in (('density', [0x3FF, 0x008, 0x3F0, 0x020], (0, 0, 0)),
+                              ('magnetization', [0x3C00, 0x0400], utils.dircos(30, -15))):
+            flat = flatten(mesh, prop)
+            nodes = mesh_nodes(mesh, prop)
+            props = flat.density[:, None] if prop == 'density' else flat.magnetization
+            for m in sets:
+                got = mesh_forward(hostsim, m, xp, yp, zp, nodes, f)
+                fields = [NAMES[i] for i in range(14) if m >> i & 1]
+                for c, fld in enumerate(fields):
+                    pr = props if fld != 'tf' else np.hstack([props, np.tile(f, (props.shape[0], 1))])
+                    ref = oracle.model(fld, xp, yp, zp, flat.bounds, pr, scale=1.0)
+                    cond = oracle.condition(fld, xp, yp, zp, flat.bounds, pr, scale=1.0)
+                    assert_parity(got[c], ref, cond, C_FLOOR_FAST,
+                                  'nodes %s %s z=%s set 0x%x' % (shape, fld, z0, m))
+    # uniform density: interior node weights vanish, only the hull is evaluated
+    mesh = mesher.PrismMesh((0, 1000, 0, 1000, 0, 500), (5, 6, 7))
+    mesh.addprop('density', 300.0 * np.ones(mesh.size))
+    nodes = mesh_nodes(mesh, 'density')
+    assert np.count_nonzero(nodes.weights[0]) == 8

@@ -26,7 +26,8 @@ def main():
         k = int(sys.argv[sys.argv.index("--points") + 1])
         for key in ("xp", "yp", "zp"):
             w[key] = np.ascontiguousarray(w[key][:k])
-    with prism.Model(w['model'], w['prop'], keep_all=w['prop'] is None, fvec=w['fvec']) as model:
+    with prism.Model(w['model'], w['prop'], keep_all=w['prop'] is None, fvec=w['fvec'],
+                     node_sharing="--per-cell" not in sys.argv) as model:
         for _ in range(reps):
             t0 = time.perf_counter()
             if w['kind'] == 'jacobian':
