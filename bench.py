@@ -16,6 +16,8 @@ data-path collective); value = all pairs of all ranks / max-over-ranks device ti
              from CUDA events on the library's own stream, summed over the K steps.
   e2e      : the public Python API (prism.fields) with HOST numpy arrays: mesh
              flattening, model upload, point H2D, kernels, result D2H, every step.
+  evaluation : regular PrismMesh models (C2, C3) are evaluated once per mesh NODE
+             (csrc/prism_mesh.cuh); --per-cell forces the general per-cell kernels.
   roofline : FP64 pipe.  achieved = pairs/s x F, F = SURVEY 8(d)'s fused-minimal FLOP
              per pair of the REFERENCE formulation (what the answer costs with
              libdevice-grade log/atan2 per corner); peak = DFMA-chain rate measured
@@ -65,6 +67,9 @@ WORK = {
 DRAM_TRAFFIC_PER_LAUNCH = {"c2": 3.9e6, "c2a": 3.9e6, "c3": None, "c4": None, "c5": None, "c5t": None}
 EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3,
                           "c5full": 318.5, "c5tfull": 523.3, "c4full": 318.5}   # profiles/r01_*
+# the same for the node-sharing kernel of regular meshes, per CELL x point pair
+# (profiles/r01_c2_tensor_nodes.txt, r01_c3_mag4_nodes.txt)
+EXECUTED_FP64_PER_PAIR_NODES = {"c2": 221.2, "c2a": 221.2, "c3": 231.7}
 
 
 # --------------------------------------------------------------------------
@@ -303,6 +308,7 @@ def run_gpu(args):
     import ctypes
 
     world, rank, local = dist_setup(args.gpus)
+    prism.NODE_SHARING = not args.per_cell          # the e2e leg goes through prism.fields
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -411,7 +417,8 @@ def run_gpu(args):
         per_gpu = value / world
         achieved = per_gpu * wk['flop'] / 1e12
         peak = sustained.value if ms_per_step > 500 else burst.value
-        executed = EXECUTED_FP64_PER_PAIR.get(args.workload)
+        executed = (EXECUTED_FP64_PER_PAIR_NODES if model.nodes is not None and w['kind'] == 'forward'
+                    else EXECUTED_FP64_PER_PAIR).get(args.workload)
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak if peak else None,
