@@ -60,6 +60,18 @@ _SIGNATURES = {
     "fb200_fp64_peak": ([ctypes.c_int, _d, ctypes.POINTER(_d), ctypes.POINTER(_d)], ctypes.c_int),
     "fb200_flush_l2": ([ctypes.c_int], ctypes.c_int),
     "fb200_debug_math": ([ctypes.c_int, ctypes.c_int, _dp, _dp, _i64, _dp], ctypes.c_int),
+    "fb200_harvest_create": ([ctypes.c_int, ctypes.c_int, ctypes.POINTER(_i64),
+                              ctypes.POINTER(ctypes.c_int)] + [_dp] * 7
+                             + [ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
+    "fb200_harvest_destroy": ([ctypes.c_void_p], ctypes.c_int),
+    "fb200_harvest_effects": ([ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp,
+                               ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64), ctypes.c_uint32],
+                              ctypes.c_int),
+    "fb200_harvest_accrete": ([ctypes.c_void_p, _i64], ctypes.c_int),
+    "fb200_harvest_evaluate": ([ctypes.c_void_p, _i64, ctypes.POINTER(_i64), _dp, _dp], ctypes.c_int),
+    "fb200_harvest_predicted": ([ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)], ctypes.c_int),
+    "fb200_harvest_effect": ([ctypes.c_void_p, _i64, _dp], ctypes.c_int),
+    "fb200_harvest_launches": ([ctypes.c_void_p], _i64),
 }
 for _name in ("potential", "gx", "gy", "gz", "gxx", "gxy", "gxz", "gyy", "gyz", "gzz"):
     _SIGNATURES["fb200_prism_" + _name] = (_PRISM_GRAVITY, ctypes.c_int)

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/fatiando_b200.h"
+#include "abi_internal.h"
 #include "prism_fastmath.cuh"
 #include "prism_launch.h"
 #include "prism_masks.h"
@@ -34,6 +35,9 @@ static int fail(int code, const std::string &msg)
     g_err = msg;
     return code;
 }
+
+// for the other translation units of the library (abi_internal.h)
+int fb200::set_error(int code, const std::string &msg) { return fail(code, msg); }
 
 #define CK(call)                                                                   \
     do {                                                                           \

@@ -55,3 +55,47 @@ def gaussian2d(x, y, sigma_x, sigma_y, x0=0, y0=0, angle=0.0):
     xhat = x - x0
     yhat = y - y0
     return numpy.exp(-(a * xhat ** 2 + 2. * b * xhat * yhat + c * yhat ** 2))
+
+
+class SparseList(object):
+    """
+    A fixed-length list that stores only the entries that were set; everything
+    else reads as 0.0 (the container of the harvester's estimates,
+    utils.py:351-430 of the reference).
+
+    >>> l = SparseList(5)
+    >>> l[3] = 42.0
+    >>> len(l), l[1], l[3]
+    (5, 0.0, 42.0)
+    >>> l[1] += 3.0
+    >>> list(l)
+    [0.0, 3.0, 0.0, 42.0, 0.0]
+    """
+
+    def __init__(self, size, elements=None):
+        self.size = size
+        self.elements = {} if elements is None else elements
+
+    def __str__(self):
+        return str(self.elements)
+
+    def __len__(self):
+        return self.size
+
+    def __iter__(self):
+        return (self[i] for i in range(self.size))
+
+    def _position(self, index):
+        if index < 0:
+            index += self.size
+        if index < 0 or index >= self.size:
+            raise IndexError('index out of range')
+        return index
+
+    def __getitem__(self, index):
+        return self.elements.get(self._position(index), 0.0)
+
+    def __setitem__(self, index, value):
+        if index >= self.size:
+            raise IndexError('index out of range')
+        self.elements[index] = value

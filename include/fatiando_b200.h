@@ -210,6 +210,45 @@ int fb200_prism_bz(const double *xp, const double *yp, const double *zp, int64_t
                    double x1, double x2, double y1, double y2, double z1, double z2,
                    double mx, double my, double mz, double *res); /* _prism.pyx:166 */
 
+/* ---- planting inversion: device-resident effect engine -------------------
+ * What fatiando/gravmag/harvester.py keeps in Python objects and numpy loops:
+ * the "effect" of every candidate cell on every data set
+ * (Data.effect, harvester.py:690-694 and :958-962, called from _calc_effect
+ * :487-493) and, per accretion, the data-misfit and shape-of-anomaly terms of
+ * predicted + effect for every candidate (_misfitfunc :447-456, _shapefunc
+ * :434-444, looped by _grow :412-431).  Data sets are concatenated: sizes[d]
+ * points each, `fields[d]` the fb200_field they hold, fvec = 3 direction
+ * cosines per data set (only read for FB200_TF), scale[d] the unit factor.
+ * `weights` has one entry per datum.  The engine owns `predicted` (float32,
+ * like harvester.py:401) and an effect store addressed by caller-chosen ROW
+ * numbers (a free-list on the host side keeps them dense).                   */
+typedef struct fb200_harvest fb200_harvest;
+int fb200_harvest_create(int device, int ndata, const int64_t *sizes, const int *fields,
+                         const double *x, const double *y, const double *z,
+                         const double *observed, const double *weights,
+                         const double *fvec /* 3*ndata or NULL */, const double *scale,
+                         fb200_harvest **out);
+int fb200_harvest_destroy(fb200_harvest *h);
+/* effect rows of ncells cells: bounds = 6 doubles per cell (x1,x2,y1,y2,z1,z2);
+ * density[c] (NaN = the cell's props have no 'density' -> zero effect on
+ * gravity data, harvester.py:691-692); magnetization = 3 doubles per cell with
+ * mag_kind[c] 0 = none, 1 = scalar in [3c] (taken along the data set's
+ * inducing field, prism.py:641-645), 2 = vector.  flags: 0 or
+ * FB200_REFERENCE_ORDER.                                                     */
+int fb200_harvest_effects(fb200_harvest *h, int ncells, const double *bounds,
+                          const double *density, const double *magnetization,
+                          const int *mag_kind, const int64_t *rows, uint32_t flags);
+/* predicted += effect[row], rounded to float32 (harvester.py:373-374)        */
+int fb200_harvest_accrete(fb200_harvest *h, int64_t row);
+/* for each candidate row (or -1 = the current estimate alone) and data set:
+ * misfit[c*ndata+d] = sqrt(sum w r r)/||obs||, shape[c*ndata+d] =
+ * ||alpha obs - pred||, pred = predicted + effect[row]                       */
+int fb200_harvest_evaluate(fb200_harvest *h, int64_t ncand, const int64_t *rows,
+                           double *misfit, double *shape);
+int fb200_harvest_predicted(fb200_harvest *h, float *out /* all data sets */);
+int fb200_harvest_effect(fb200_harvest *h, int64_t row, double *out /* all data sets */);
+int64_t fb200_harvest_launches(const fb200_harvest *h);
+
 /* ---- measurement helpers (used by bench.py; not part of the data path) --
  * Device time in milliseconds of the kernels launched by the most recent
  * fb200_forward / fb200_jacobian call on this model (CUDA events on the
