@@ -38,6 +38,9 @@ _SIGNATURES = {
                            ctypes.c_int),
     "fb200_model_attach_mesh": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
                                 + [_dp] * 8, ctypes.c_int),
+    "fb200_model_attach_surface": ([ctypes.c_void_p, _i64] + [_dp] * 7 + [_i64] + [_dp] * 5,
+                                   ctypes.c_int),
+    "fb200_model_set_hazard_planes": ([ctypes.c_void_p, _i64, _dp, _i64, _dp, _i64, _dp], ctypes.c_int),
     "fb200_model_destroy": ([ctypes.c_void_p], ctypes.c_int),
     "fb200_model_size": ([ctypes.c_void_p], _i64),
     "fb200_model_device": ([ctypes.c_void_p], ctypes.c_int),

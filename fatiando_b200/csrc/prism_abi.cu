@@ -84,6 +84,16 @@ struct fb200_model {
     double *d_wdens = nullptr;                          // node weights of the density
     double *d_wmag[3] = {nullptr, nullptr, nullptr};    // ... of mx, my, mz
     double shift[3] = {0.0, 0.0, 0.0};
+    // optional surface form of a relief (prism_face.cuh): top faces + reference-plane nodes
+    bool has_surface = false;
+    int64_t nfaces = 0, nsnodes = 0;
+    double *d_face[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x1 x2 y1 y2 zf zo w
+    double *d_snode[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // xn shx yn shy zn zn w
+    int *d_flag = nullptr;
+    // cell walls whose coordinate the reference computes differently from the two sides
+    // (x2 of one cell != x1 of the next, one ulp apart): see fb200_model_set_hazard_planes
+    double *d_hazard[3] = {nullptr, nullptr, nullptr};
+    int64_t n_hazard[3] = {0, 0, 0};
     double last_ms = 0.0;
     int last_launches = 0;
     std::mutex lock;   // one call at a time per handle
@@ -176,6 +186,26 @@ __global__ void canonical_zero_kernel(double *p, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = p[i] + 0.0;
+}
+
+// *flag = 1 when some coordinate c[l] lies within a few ulp of one of the (sorted) planes
+__global__ void near_plane_kernel(const double *c, int64_t n, const double *planes, int64_t np, int *flag)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const double v = c[l];
+    int64_t lo = 0, hi = np;            // first plane >= v
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (planes[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    bool near = false;
+    for (int64_t k = lo - 1; k <= lo; ++k) {
+        if (k < 0 || k >= np) continue;
+        const double p = planes[k];
+        near = near || fabs(v - p) <= 0x1p-49 * fmax(fabs(v), fabs(p));     // 8 ulp
+    }
+    if (near) *flag = 1;
 }
 
 __global__ void fill_kernel(double *p, int64_t n, double v)
@@ -283,6 +313,11 @@ extern "C" int fb200_model_destroy(fb200_model *model)
     if (model->d_nodes) cudaFreeAsync(model->d_nodes, st);
     if (model->d_wdens) cudaFreeAsync(model->d_wdens, st);
     for (double *p : model->d_wmag) if (p) cudaFreeAsync(p, st);
+    for (double *p : model->d_face) if (p) cudaFreeAsync(p, st);
+    for (int r = 0; r < 7; ++r)
+        if (model->d_snode[r] && r != 5) cudaFreeAsync(model->d_snode[r], st);   // row 5 aliases row 4
+    if (model->d_flag) cudaFreeAsync(model->d_flag, st);
+    for (double *p : model->d_hazard) if (p) cudaFreeAsync(p, st);
     StreamSet set;
     set.stream = model->stream; set.ev0 = model->ev0; set.ev1 = model->ev1;
     release_streams(model->device, set);
@@ -384,6 +419,83 @@ extern "C" int fb200_model_attach_mesh(fb200_model *mod, int nx, int ny, int nz,
     for (int r = 0; r < 3; ++r) mod->shift[r] = 0.00001 * cell_size[r];   // _prism.pyx:328-329
     CK(cudaStreamSynchronize(mod->stream));
     mod->has_mesh = true;
+    return FB200_OK;
+}
+
+extern "C" int fb200_model_attach_surface(fb200_model *mod, int64_t nfaces, const double *x1,
+                                          const double *x2, const double *y1, const double *y2,
+                                          const double *z_face, const double *z_other,
+                                          const double *w_face, int64_t nnodes, const double *xn,
+                                          const double *yn, const double *zn, const double *w_node,
+                                          const double *cell_size)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    if (nfaces < 1 || nnodes < 0) return fail(FB200_EINVAL, "surface needs at least one face");
+    if (!x1 || !x2 || !y1 || !y2 || !z_face || !z_other || !w_face || !cell_size)
+        return fail(FB200_EINVAL, "NULL face array");
+    if (nnodes > 0 && (!xn || !yn || !zn || !w_node)) return fail(FB200_EINVAL, "NULL node array");
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    if (mod->has_surface) return fail(FB200_EINVAL, "a surface is already attached to this model");
+    const int64_t f_pad = (nfaces + TILE - 1) / TILE * TILE;
+    const double *face_src[7] = {x1, x2, y1, y2, z_face, z_other, w_face};
+    for (int r = 0; r < 7; ++r) {
+        int rc = upload(&mod->d_face[r], face_src[r], nfaces, f_pad, mod->stream);
+        if (rc != FB200_OK) return rc;
+        if (r < 6) canonical_zero_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, mod->stream>>>(mod->d_face[r], nfaces);
+    }
+    if (nnodes > 0) {
+        const int64_t n_pad = (nnodes + TILE - 1) / TILE * TILE;
+        std::vector<double> shx((size_t)nnodes, 0.00001 * cell_size[0]);   // _prism.pyx:328-329
+        std::vector<double> shy((size_t)nnodes, 0.00001 * cell_size[1]);
+        const double *node_src[7] = {xn, shx.data(), yn, shy.data(), zn, nullptr, w_node};
+        for (int r = 0; r < 7; ++r) {
+            if (r == 5) { mod->d_snode[5] = mod->d_snode[4]; continue; }
+            int rc = upload(&mod->d_snode[r], node_src[r], nnodes, n_pad, mod->stream);
+            if (rc != FB200_OK) return rc;
+            if (r == 0 || r == 2 || r == 4)
+                canonical_zero_kernel<<<(unsigned)((nnodes + 255) / 256), 256, 0, mod->stream>>>(mod->d_snode[r], nnodes);
+        }
+        CK(cudaStreamSynchronize(mod->stream));      // shx / shy are locals
+    }
+    if (!mod->d_flag) CK(cudaMallocAsync((void **)&mod->d_flag, sizeof(int), mod->stream));
+    CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+    CK(cudaStreamSynchronize(mod->stream));
+    mod->nfaces = nfaces;
+    mod->nsnodes = nnodes;
+    mod->has_surface = true;
+    return FB200_OK;
+}
+
+extern "C" int fb200_model_set_hazard_planes(fb200_model *mod, int64_t nx, const double *xw,
+                                             int64_t ny, const double *yw, int64_t nz,
+                                             const double *zw)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    const int64_t cnt[3] = {nx, ny, nz};
+    const double *src[3] = {xw, yw, zw};
+    for (int a = 0; a < 3; ++a)
+        if (cnt[a] < 0 || (cnt[a] > 0 && !src[a])) return fail(FB200_EINVAL, "bad hazard plane array");
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    for (int a = 0; a < 3; ++a) {
+        if (mod->d_hazard[a]) { cudaFreeAsync(mod->d_hazard[a], mod->stream); mod->d_hazard[a] = nullptr; }
+        mod->n_hazard[a] = 0;
+        if (cnt[a] == 0) continue;
+        std::vector<double> sorted(src[a], src[a] + cnt[a]);
+        std::sort(sorted.begin(), sorted.end());
+        CK(cudaMallocAsync((void **)&mod->d_hazard[a], (size_t)cnt[a] * 8, mod->stream));
+        CK(cudaMemcpyAsync(mod->d_hazard[a], sorted.data(), (size_t)cnt[a] * 8, cudaMemcpyHostToDevice, mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+        mod->n_hazard[a] = cnt[a];
+    }
+    if (!mod->d_flag) {
+        CK(cudaMallocAsync((void **)&mod->d_flag, sizeof(int), mod->stream));
+        CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+    }
     return FB200_OK;
 }
 
@@ -507,6 +619,68 @@ static int run_set_mesh(fb200_model *mod, uint32_t set, uint32_t request, bool a
     rc = reduce_split(mod, nc, nsplit, n, ld_p, a.scale, a.out_row, d_out, ld_out);
     if (rc != FB200_OK) return rc;
     mod->last_launches += 2;
+    return FB200_OK;
+}
+
+// Surface form of a relief (gravity sets): top faces and reference-plane nodes write
+// partial sums side by side, one fixed-order reduction adds them.
+static int run_set_surface(fb200_model *mod, uint32_t set, uint32_t request, bool allow_split,
+                           const double *d_xp, const double *d_yp, const double *d_zp, int64_t n,
+                           const double *scale, double *d_out, int64_t ld_out)
+{
+    ForwardArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.xp = d_xp; a.yp = d_yp; a.zp = d_zp; a.n = n;
+    a.flag = mod->d_flag;
+    const int nc = popc(set);
+    int c = 0;
+    for (int f = 0; f < F_COUNT; ++f) {
+        if (!(set & bit(f))) continue;
+        const int row = popc(request & (bit(f) - 1));
+        a.out_row[c] = row;
+        a.scale[c] = scale ? scale[row] : 1.0;
+        ++c;
+    }
+    const int64_t blocks_x = (n + FWD_THREADS - 1) / FWD_THREADS;
+    auto split_of = [&](int64_t m, int64_t *chunk) {
+        const int64_t tiles = (m + TILE - 1) / TILE;
+        int64_t ns = 1;
+        if (allow_split) {
+            const int64_t target = (int64_t)mod->sm_count * 20;
+            ns = std::min<int64_t>(std::max<int64_t>(1, (target + blocks_x - 1) / blocks_x), tiles);
+            ns = std::min<int64_t>(ns, 32000);
+        }
+        *chunk = ((tiles + ns - 1) / ns) * TILE;
+        return (m + *chunk - 1) / *chunk;
+    };
+    int64_t chunk_f = TILE, chunk_n = TILE;
+    const int64_t ns_f = split_of(mod->nfaces, &chunk_f);
+    const int64_t ns_n = mod->nsnodes > 0 ? split_of(mod->nsnodes, &chunk_n) : 0;
+    const int64_t ns = ns_f + ns_n;
+    const int64_t ld_p = (n + 31) / 32 * 32;
+    int rc = grow(&mod->d_part, &mod->part_cap, (size_t)ns * nc * ld_p, mod->stream);
+    if (rc != FB200_OK) return rc;
+    a.ld = ld_p;
+    a.nsplit = (int)std::max<int64_t>(ns, 2);          // always the partial-sum output mode
+    for (int r = 0; r < 6; ++r) a.model.b[r] = mod->d_face[r];
+    a.model.p[0] = mod->d_face[6];
+    a.model.m = mod->nfaces;
+    a.chunk = chunk_f;
+    a.out = mod->d_part;
+    CK(launch_forward_face(set, a, (int)ns_f, mod->stream));
+    mod->last_launches += 1;
+    if (ns_n > 0) {
+        for (int r = 0; r < 6; ++r) a.model.b[r] = mod->d_snode[r];
+        a.model.p[0] = mod->d_snode[6];
+        a.model.m = mod->nsnodes;
+        a.chunk = chunk_n;
+        a.out = mod->d_part + (size_t)ns_f * nc * ld_p;
+        CK(launch_forward_node(set, a, (int)ns_n, mod->stream));
+        mod->last_launches += 1;
+    }
+    rc = reduce_split(mod, nc, ns, n, ld_p, a.scale, a.out_row, d_out, ld_out);
+    if (rc != FB200_OK) return rc;
+    mod->last_launches += 1;
     return FB200_OK;
 }
 
@@ -634,16 +808,49 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         CK(cudaEventRecord(mod->ev0, mod->stream));
         // a regular mesh with node weights attached: node-sharing kernel, unless the
         // caller overrides the property, wants the reference order or the per-cell path
-        const bool nodes_ok = mod->has_mesh && !exact && !init && !(flags & FB200_PER_CELL);
-        if (gmask) {
-            const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
-            for (uint32_t set : cover(gmask, kGravitySets)) {
-                int rc = use_nodes
-                    ? run_set_mesh(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, fvec, scale, d_out, ld)
-                    : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
-                              dens_override, fvec, scale, d_init, d_out, ld);
-                if (rc != FB200_OK) return rc;
+        bool nodes_ok = mod->has_mesh && !exact && !init && !(flags & FB200_PER_CELL);
+        // a relief with its surface form attached: same conditions, gravity only
+        bool surface = mod->has_surface && gmask && !exact && !init && !(flags & FB200_PER_CELL) &&
+                       !dens_override;
+        // Where the reference's two cells disagree on a shared wall by an ulp, a point IN that
+        // wall gets direction-dependent terms (atan2 of +-0 denominators) that do not cancel in
+        // the reference; the merged forms cannot reproduce that, the per-cell kernels do.
+        if ((nodes_ok || surface) && (mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2])) {
+            CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+            const double *coord[3] = {d_xp, d_yp, d_zp};
+            for (int ax = 0; ax < 3; ++ax) {
+                if (!mod->n_hazard[ax]) continue;
+                near_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(
+                    coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag);
+                CK(cudaGetLastError());
             }
+            int raised = 0;
+            CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+            CK(cudaStreamSynchronize(mod->stream));
+            if (raised) nodes_ok = surface = false;
+        }
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (surface) CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+            if (gmask) {
+                const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
+                for (uint32_t set : cover(gmask, kGravitySets)) {
+                    int rc = surface
+                        ? run_set_surface(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, scale, d_out, ld)
+                        : use_nodes
+                        ? run_set_mesh(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, fvec, scale, d_out, ld)
+                        : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
+                                  dens_override, fvec, scale, d_init, d_out, ld);
+                    if (rc != FB200_OK) return rc;
+                }
+            }
+            if (!surface) break;
+            // a merged reference-plane node met the thickness-dependent shift of gxz / gyz
+            // (prism_face.cuh: EvalNode): evaluate this call cell by cell instead
+            int raised = 0;
+            CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+            CK(cudaStreamSynchronize(mod->stream));
+            if (!raised) break;
+            surface = false;
         }
         if (mmask) {
             const bool use_nodes = nodes_ok && mod->d_wmag[0] && !pmag_override;

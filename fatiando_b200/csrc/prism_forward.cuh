@@ -146,8 +146,13 @@ forward_kernel(const ForwardArgs a)
                 p0 = sp[s][6][q];
                 if (MAG) { p1 = sp[s][6 + (NP > 1 ? 1 : 0)][q]; p2 = sp[s][6 + (NP > 2 ? 2 : 0)][q]; }
             }
-            Eval::template pair<MASK>(acc, xp, yp, zp, sp[s][0][q], sp[s][1][q], sp[s][2][q],
-                                      sp[s][3][q], sp[s][4][q], sp[s][5][q], p0, p1, p2, f);
+            if constexpr (Eval::NEEDS_FLAG)
+                Eval::template pair_flag<MASK>(acc, xp, yp, zp, sp[s][0][q], sp[s][1][q], sp[s][2][q],
+                                               sp[s][3][q], sp[s][4][q], sp[s][5][q], p0, p1, p2, f,
+                                               a.flag);
+            else
+                Eval::template pair<MASK>(acc, xp, yp, zp, sp[s][0][q], sp[s][1][q], sp[s][2][q],
+                                          sp[s][3][q], sp[s][4][q], sp[s][5][q], p0, p1, p2, f);
         }
         // release the stage; the last warp out refills it with the tile two ahead
         __syncwarp();
@@ -176,10 +181,12 @@ forward_kernel(const ForwardArgs a)
 }
 
 // Generic launcher body used by the per-group translation units.
+// grid_y = 0: one block row per prism chunk (a.nsplit); otherwise the caller's own
+// count (several launches sharing one set of partial sums, prism_abi.cu: run_set_surface)
 template <uint32_t MASK, class Eval>
-inline cudaError_t launch_forward_t(const ForwardArgs &a, cudaStream_t stream)
+inline cudaError_t launch_forward_t(const ForwardArgs &a, cudaStream_t stream, int grid_y = 0)
 {
-    dim3 grid((unsigned)((a.n + FWD_THREADS - 1) / FWD_THREADS), (unsigned)a.nsplit);
+    dim3 grid((unsigned)((a.n + FWD_THREADS - 1) / FWD_THREADS), (unsigned)(grid_y ? grid_y : a.nsplit));
     forward_kernel<MASK, Eval><<<grid, FWD_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }

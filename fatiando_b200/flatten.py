@@ -33,9 +33,11 @@ class FlatModel(object):
     * total : number of entries of the input (kept + dropped)
     * nodes : :class:`MeshNodes` when the input was a regular ``PrismMesh``
       carrying the property (its node-sharing form), else ``None``
+    * surface : :class:`ReliefSurface` when the input was a ``PrismRelief`` on a
+      tight regular grid carrying a density, else ``None``
     """
 
-    def __init__(self, bounds, density, magnetization, index, total, nodes=None):
+    def __init__(self, bounds, density, magnetization, index, total, nodes=None, surface=None):
         self.bounds = [np.ascontiguousarray(b, dtype=np.float64) for b in bounds]
         self.density = None if density is None else np.ascontiguousarray(density, dtype=np.float64)
         self.magnetization = (None if magnetization is None
@@ -43,6 +45,7 @@ class FlatModel(object):
         self.index = np.ascontiguousarray(index, dtype=np.int64)
         self.total = int(total)
         self.nodes = nodes
+        self.surface = surface
 
     @property
     def size(self):
@@ -135,11 +138,23 @@ class MeshNodes(object):
       Masked cells count as zero.
     """
 
-    def __init__(self, shape, xn, yn, zn, cell_size, weights):
+    def __init__(self, shape, xn, yn, zn, cell_size, weights, hazard=None):
         self.shape = shape
         self.xn, self.yn, self.zn = xn, yn, zn
         self.cell_size = np.array(cell_size, dtype=np.float64)
         self.weights = weights
+        self.hazard = hazard if hazard is not None else [np.zeros(0)] * 3
+
+
+def _mismatched_walls(upper_of_lower_cell, lower_of_upper_cell):
+    """
+    Coordinates (both variants) of the interior walls that the reference computes
+    differently from their two sides -- see fb200_model_set_hazard_planes.
+    """
+    a = np.asarray(upper_of_lower_cell, dtype=np.float64)
+    b = np.asarray(lower_of_upper_cell, dtype=np.float64)
+    bad = a != b
+    return np.ascontiguousarray(np.concatenate([a[bad], b[bad]]))
 
 
 def _node_coordinates(b0, d, n):
@@ -191,9 +206,78 @@ def mesh_nodes(mesh, prop, fvec=None):
     if not all(np.all(np.isfinite(ch)) for ch in channels):
         return None
     b = mesh.bounds
-    return MeshNodes((nz, ny, nx), _node_coordinates(b[0], dx, nx), _node_coordinates(b[2], dy, ny),
-                     _node_coordinates(b[4], dz, nz), (dx, dy, dz),
-                     [_node_weights(ch, (nz, ny, nx)) for ch in channels])
+    nodes = [_node_coordinates(b[0], dx, nx), _node_coordinates(b[2], dy, ny),
+             _node_coordinates(b[4], dz, nz)]
+    # x2 = x1 + dx of cell i against x1 = b0 + dx*(i+1) of cell i+1 (mesh.py:629-634)
+    hazard = [_mismatched_walls(c[:-2] + d, c[1:-1]) for c, d in zip(nodes, (dx, dy, dz))]
+    return MeshNodes((nz, ny, nx), nodes[0], nodes[1], nodes[2], (dx, dy, dz),
+                     [_node_weights(ch, (nz, ny, nx)) for ch in channels], hazard)
+
+
+class ReliefSurface(object):
+    """
+    Surface form of a ``PrismRelief`` on a tight regular grid (csrc/prism_face.cuh).
+
+    * faces : seven float64 arrays ``x1, x2, y1, y2, z_face, z_other, w`` -- one top
+      face per cell, ``w = -rho`` with ``rho`` the cell's density once the sign rule
+      of ``PrismRelief.addprop`` (mesh.py:484-488) is undone
+    * nodes : four float64 arrays ``xn, yn, zn, w`` -- reference-plane corners merged
+      over the cells that share them, ``w`` = signed 2x2 sum of ``rho``; zero-weight
+      nodes are dropped
+    * cell_size : (dx, dy)
+    """
+
+    def __init__(self, faces, nodes, cell_size, hazard=None):
+        self.faces = [np.ascontiguousarray(a, dtype=np.float64) for a in faces]
+        self.nodes = [np.ascontiguousarray(a, dtype=np.float64) for a in nodes]
+        self.cell_size = np.array(cell_size, dtype=np.float64)
+        self.hazard = hazard if hazard is not None else [np.zeros(0)] * 3
+
+
+def relief_surface(relief, prop='density'):
+    """
+    :class:`ReliefSurface` of ``relief``, or ``None`` when it does not apply: not a
+    ``PrismRelief`` with a per-cell density, the nodes are not a regular grid, or the
+    cells do not tile it (spacing differs from the cell size by more than rounding).
+    """
+    if prop != 'density' or not _is_prism_relief(relief) or 'density' not in relief.props:
+        return None
+    n = int(relief.size)
+    dens, _, generic = _property_arrays({'density': relief.props['density']}, n)
+    if generic or n == 0 or not np.all(np.isfinite(dens)):
+        return None
+    x = np.asarray(relief.x, dtype=np.float64)
+    y = np.asarray(relief.y, dtype=np.float64)
+    z = np.asarray(relief.z, dtype=np.float64)
+    dx, dy, ref = float(relief.dx), float(relief.dy), float(relief.ref)
+    if not (dx > 0 and dy > 0 and np.all(np.isfinite(x)) and np.all(np.isfinite(y))
+            and np.all(np.isfinite(z))):
+        return None
+    xs, ix = np.unique(x, return_inverse=True)
+    ys, iy = np.unique(y, return_inverse=True)
+    nx, ny = xs.size, ys.size
+    if nx * ny != n or np.unique(iy * nx + ix).size != n:
+        return None
+    bounds = _relief_bounds(relief)
+    # neighbouring cells must share their edge up to rounding: xs[a] + dx/2 == xs[a+1] - dx/2
+    tol = 8 * np.finfo(float).eps
+    for c, h, big in ((xs, 0.5 * dx, np.abs(xs).max()), (ys, 0.5 * dy, np.abs(ys).max())):
+        if c.size > 1 and np.any(np.abs((c[:-1] + h) - (c[1:] - h)) > tol * max(big, h)):
+            return None
+    rho = np.where(z <= ref, dens, -dens)
+    grid = np.zeros((ny + 2, nx + 2))
+    grid[iy + 1, ix + 1] = rho
+    # node (a, b) is the (x2, y2) corner of cell (a-1, b-1): + ; of (a, b-1) and (a-1, b): - ; (a, b): +
+    w = grid[:-1, :-1] - grid[:-1, 1:] - grid[1:, :-1] + grid[1:, 1:]
+    xn = np.concatenate([xs - 0.5 * dx, [xs[-1] + 0.5 * dx]])
+    yn = np.concatenate([ys - 0.5 * dy, [ys[-1] + 0.5 * dy]])
+    b, a = np.nonzero(w)
+    nodes = [xn[a], yn[b], np.full(a.size, ref), w[b, a]]
+    faces = [bounds[0], bounds[1], bounds[2], bounds[3], z, np.full(n, ref), -rho]
+    # xc + dx/2 of one node against xc - dx/2 of the next (mesh.py:447-450)
+    hazard = [_mismatched_walls(xs[:-1] + 0.5 * dx, xs[1:] - 0.5 * dx),
+              _mismatched_walls(ys[:-1] + 0.5 * dy, ys[1:] - 0.5 * dy), np.zeros(0)]
+    return ReliefSurface(faces, nodes, (dx, dy), hazard)
 
 
 def flatten(prisms, prop=None, override=False, fvec=None):
@@ -236,10 +320,11 @@ def flatten(prisms, prop=None, override=False, fvec=None):
         mag = None
     if mag is not None and mag.ndim == 1:
         mag = _expand_scalar_magnetization(mag, fvec)
-    nodes = None
+    nodes = surface = None
     if prop is not None and not override and index.size:
         nodes = mesh_nodes(prisms, prop, fvec=fvec)
-    return FlatModel(bounds, dens, mag, index, total, nodes)
+        surface = relief_surface(prisms, prop)
+    return FlatModel(bounds, dens, mag, index, total, nodes, surface)
 
 
 def _expand_scalar_magnetization(values, fvec):

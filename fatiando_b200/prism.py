@@ -107,7 +107,9 @@ class Model(object):
 
     * node_sharing : for a regular ``PrismMesh`` also upload the node-sharing
       form (one kernel evaluation per mesh node instead of eight per cell,
-      csrc/prism_mesh.cuh); forward fields then use it unless an override or
+      csrc/prism_mesh.cuh), for a ``PrismRelief`` on a tight regular grid its
+      surface form (top faces + merged reference-plane nodes,
+      csrc/prism_face.cuh); forward fields then use it unless an override or
       ``per_cell=True`` is given.  Same tolerance as the per-cell path.
 
     Use as a context manager or call :meth:`close`.
@@ -131,6 +133,18 @@ class Model(object):
             _lib.dptr(flat.density), *[_lib.dptr(c) for c in cols],
             ctypes.byref(self._handle)))
         self.nodes = flat.nodes if (node_sharing and NODE_SHARING) else None
+        self.surface = flat.surface if (node_sharing and NODE_SHARING) else None
+        if self.surface is not None:
+            sf = self.surface
+            _lib.check(lib.fb200_model_attach_surface(
+                self._handle, sf.faces[0].size, *[_lib.dptr(a) for a in sf.faces],
+                sf.nodes[0].size, *[_lib.dptr(a) for a in sf.nodes], _lib.dptr(sf.cell_size)))
+        merged = self.nodes if self.nodes is not None else self.surface
+        if merged is not None and any(h.size for h in merged.hazard):
+            hz = [numpy.ascontiguousarray(h, dtype=numpy.float64) for h in merged.hazard]
+            _lib.check(lib.fb200_model_set_hazard_planes(
+                self._handle, hz[0].size, _lib.dptr(hz[0]), hz[1].size, _lib.dptr(hz[1]),
+                hz[2].size, _lib.dptr(hz[2])))
         if self.nodes is not None:
             nd = self.nodes
             nz, ny, nx = nd.shape

@@ -105,6 +105,40 @@ int fb200_model_attach_mesh(fb200_model *model, int nx, int ny, int nz,
                             const double *w_density /* nodes, or NULL */,
                             const double *w_mx, const double *w_my,
                             const double *w_mz /* nodes each, or all NULL */);
+/* Relief acceleration (optional).  Declares that the model's prisms are the
+ * cells of a PrismRelief (mesh.py:391-492) on a tight regular grid and hands
+ * over its surface form: cell c = rho_c * (G_c(ref) - G_c(z_c)), G = the
+ * 4-corner alternating sum over one horizontal face.  Faces: one per cell,
+ * x1,x2,y1,y2 (the reference's own bounds), z_face = z_c, z_other = ref,
+ * w_face = -rho_c (rho_c = the stored density, negated where z_c > ref --
+ * undoing addprop's sign rule, mesh.py:484-488).  Nodes: the reference-plane
+ * corners merged over the <= 4 cells that share them, weight = signed 2x2 sum
+ * of rho; only non-zero ones need to be listed (for a uniform density, the
+ * rim of the grid).  cell_size = (dx, dy).  fb200_forward then evaluates
+ * gravity fields from this form (about 1.4x fewer FP64 instructions) unless
+ * dens_override, FB200_REFERENCE_ORDER or FB200_PER_CELL is given; a point
+ * that would need the thickness-dependent 1e-5 shift of gxz/gyz at a merged
+ * node (it lies in the reference plane on a grid line) makes the call fall
+ * back to the per-cell kernels by itself.                                    */
+int fb200_model_attach_surface(fb200_model *model, int64_t nfaces,
+                               const double *x1, const double *x2,
+                               const double *y1, const double *y2,
+                               const double *z_face, const double *z_other,
+                               const double *w_face, int64_t nnodes,
+                               const double *xn, const double *yn, const double *zn,
+                               const double *w_node, const double *cell_size /* 2 */);
+/* Walls the merged forms above must not be trusted on.  The reference computes a
+ * wall shared by two cells once from each side (x2 = x1 + dx of one cell,
+ * x1 = b0 + dx*(i+1) of the next, mesh.py:629-634; xc +- dx/2 of neighbouring
+ * relief nodes, :447-450); where the two roundings differ, a point lying IN the
+ * wall gets atan2 terms with a zero denominator from one cell and a one-ulp
+ * denominator of either sign from the other -- they need not cancel, and the
+ * reference's answer there depends on that rounding.  Pass the coordinates of
+ * such walls (both variants); a forward call with a point within 8 ulp of one
+ * of them is evaluated by the per-cell kernels, which see the reference's own
+ * bounds.  Meshes and reliefs with exactly representable walls need none.    */
+int fb200_model_set_hazard_planes(fb200_model *model, int64_t nx, const double *xw,
+                                  int64_t ny, const double *yw, int64_t nz, const double *zw);
 int     fb200_model_destroy(fb200_model *model);
 int64_t fb200_model_size(const fb200_model *model);
 int     fb200_model_device(const fb200_model *model);

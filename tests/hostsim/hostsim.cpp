@@ -11,6 +11,7 @@
 #include "../../fatiando_b200/csrc/prism_masks.h"
 #include "../../fatiando_b200/csrc/prism_fast.cuh"
 #include "../../fatiando_b200/csrc/prism_mesh.cuh"
+#include "../../fatiando_b200/csrc/prism_face.cuh"
 
 using namespace fb200;
 
@@ -87,6 +88,42 @@ extern "C" int hostsim_mesh_forward(uint32_t mask, const double *xp, const doubl
     }
     FB200_GRAVITY_SETS(CASE)
     FB200_MAGNETIC_SETS(CASE)
+#undef CASE
+    return -1;
+}
+
+// surface form of a relief: top faces (EvalFace) + merged reference-plane nodes (EvalNode)
+template <uint32_t MASK>
+static int run_surface(const double *xp, const double *yp, const double *zp, size_t n, size_t nf,
+                       const double *const *face, size_t nn, const double *const *node,
+                       const double *cell, double *out)
+{
+    constexpr int NC = popc(MASK);
+    const double f[3] = {0.0, 0.0, 0.0};
+    int flag = 0;
+    for (size_t l = 0; l < n; ++l) {
+        double acc[NC], accn[NC];
+        for (int c = 0; c < NC; ++c) acc[c] = accn[c] = 0.0;
+        for (size_t q = 0; q < nf; ++q)
+            EvalFace::pair<MASK>(acc, xp[l], yp[l], zp[l], face[0][q], face[1][q], face[2][q],
+                                 face[3][q], face[4][q], face[5][q], face[6][q], 0.0, 0.0, f);
+        for (size_t q = 0; q < nn; ++q)
+            EvalNode::pair_flag<MASK>(accn, xp[l], yp[l], zp[l], node[0][q], 0.00001 * cell[0],
+                                      node[1][q], 0.00001 * cell[1], node[2][q], 0.0, node[3][q],
+                                      0.0, 0.0, f, &flag);
+        for (int c = 0; c < NC; ++c) out[(size_t)c * n + l] = acc[c] + accn[c];
+    }
+    return flag;
+}
+
+// returns the flag (1: some point needs the per-cell path), or -1 for an unknown mask
+extern "C" int hostsim_surface_forward(uint32_t mask, const double *xp, const double *yp,
+                                       const double *zp, size_t n, size_t nf,
+                                       const double *const *face, size_t nn,
+                                       const double *const *node, const double *cell, double *out)
+{
+#define CASE(M) if (mask == (M)) return run_surface<(M)>(xp, yp, zp, n, nf, face, nn, node, cell, out);
+    FB200_GRAVITY_SETS(CASE)
 #undef CASE
     return -1;
 }

@@ -363,6 +363,59 @@ def test_node_sharing_equals_per_cell_and_oracle(gpu_lib, oracle):
     assert_parity(got, ref, cond, C_FLOOR_FAST, 'override on a mesh')
 
 
+def test_relief_surface_form_equals_per_cell_and_oracle(gpu_lib, oracle):
+    """PrismRelief on a tight regular grid: surface form (default) against the per-cell kernels
+    and the oracle; the thickness-dependent shift case falls back by itself."""
+    from fatiando_b200 import prism, mesher, gridder
+    from fatiando_b200.flatten import flatten
+    rs = np.random.RandomState(8)
+    area, shape = (0, 8000, -1000, 5000), (19, 23)
+    x, y = gridder.regular(area, shape)
+    h = 600 * np.sin(x / 900.) * np.cos(y / 700.) + rs.uniform(-80, 80, x.size)     # crosses ref = 0
+    for variable in (False, True):
+        relief = mesher.PrismRelief(0, gridder.spacing(area, shape)[::-1], (x, y, -h))
+        relief.addprop('density', rs.uniform(2000, 3000, x.size) if variable else 2670. * np.ones(x.size))
+        flat = flatten(relief, 'density')
+        grids = [gridder.regular(area, (17, 16), z=-1500.),
+                 gridder.regular((-4e5, 4e5, -4e5, 4e5), (5, 6), z=-3e4),
+                 gridder.scatter(area, 200, z=100., seed=3),
+                 (flat.bounds[0][:64] + 0.0, flat.bounds[2][:64] + 0.0, -900. * np.ones(64))]
+        with prism.Model(relief, 'density') as model:
+            assert model.surface is not None
+            for xp, yp, zp in grids:
+                surf = model.fields(xp, yp, zp, GRAV)
+                cells = model.fields(xp, yp, zp, GRAV, per_cell=True)
+                one = model.fields(xp, yp, zp, ['gz'])
+                for f in GRAV:
+                    ref = oracle.model(f, xp, yp, zp, flat.bounds, flat.density[:, None])
+                    cond = oracle.condition(f, xp, yp, zp, flat.bounds, flat.density[:, None])
+                    assert_parity(surf[f], ref, cond, C_FLOOR_FAST, 'relief surface ' + f)
+                    assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'relief per cell ' + f)
+                assert_parity(one['gz'], oracle.model('gz', xp, yp, zp, flat.bounds, flat.density[:, None]),
+                              oracle.condition('gz', xp, yp, zp, flat.bounds, flat.density[:, None]),
+                              C_FLOOR_FAST, 'relief surface gz alone')
+            # points IN the reference plane on grid lines through the rim nodes: gxz / gyz need a
+            # cell's own thickness there -> the call evaluates per cell (bit-identical to it)
+            sf = model.surface
+            xp = np.repeat(sf.nodes[0][:2], 3)
+            yp = np.repeat(sf.nodes[1][:2], 3) + np.tile([7000., -9000., 12000.], 2)
+            zp = np.zeros(6)
+            a = model.fields(xp, yp, zp, ['gxz', 'gyz', 'gz'])
+            b = model.fields(xp, yp, zp, ['gxz', 'gyz', 'gz'], per_cell=True)
+            for f in a:
+                assert np.array_equal(a[f], b[f]), f
+    # the drop-in functions use it too, and an override bypasses it
+    xp, yp, zp = gridder.regular(area, (9, 8), z=-1200.)
+    got = prism.gz(xp, yp, zp, relief)
+    ref = oracle.model('gz', xp, yp, zp, flat.bounds, flat.density[:, None])
+    cond = oracle.condition('gz', xp, yp, zp, flat.bounds, flat.density[:, None])
+    assert_parity(got, ref, cond, C_FLOOR_FAST, 'prism.gz on a relief')
+    got = prism.gzz(xp, yp, zp, relief, dens=300.)
+    ref = oracle.model('gzz', xp, yp, zp, flat.bounds, np.full((flat.size, 1), 300.))
+    cond = oracle.condition('gzz', xp, yp, zp, flat.bounds, np.full((flat.size, 1), 300.))
+    assert_parity(got, ref, cond, C_FLOOR_FAST, 'override on a relief')
+
+
 def test_negative_zero_bounds_and_points_on_planes(gpu_lib, oracle):
     """-0.0 bounds (e.g. z = -1*0.0 from a flat relief) with points in those planes:
     the reference tests `x < 0`, false for -0.0; the kernel reads sign bits, so the

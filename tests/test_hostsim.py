@@ -221,3 +221,67 @@ def test_node_sharing_matches_the_per_cell_reference(hostsim, oracle):
     mesh.addprop('density', 300.0 * np.ones(mesh.size))
     nodes = mesh_nodes(mesh, 'density')
     assert np.count_nonzero(nodes.weights[0]) == 8
+
+
+def surface_forward(H, mask, xp, yp, zp, surf):
+    xp, yp, zp = (np.ascontiguousarray(a, dtype=float) for a in (xp, yp, zp))
+    out = np.zeros((bin(mask).count('1'), xp.size))
+    farr = (dp * 7)(*[_p(a) for a in surf.faces])
+    narr = (dp * 4)(*[_p(a) for a in surf.nodes])
+    flag = H.hostsim_surface_forward(ctypes.c_uint32(mask), _p(xp), _p(yp), _p(zp),
+                                     ctypes.c_size_t(xp.size), ctypes.c_size_t(surf.faces[0].size), farr,
+                                     ctypes.c_size_t(surf.nodes[0].size), narr, _p(surf.cell_size), _p(out))
+    assert flag >= 0
+    return out, flag
+
+
+def test_relief_surface_form_matches_the_per_cell_reference(hostsim, oracle):
+    """A PrismRelief as top faces + merged reference-plane nodes (csrc/prism_face.cuh) against
+    the oracle's per-cell loop: relief crossing the reference level, uniform and variable
+    density, points above, far away, between the cells' heights and on grid lines."""
+    from fatiando_b200 import mesher, gridder
+    from fatiando_b200.flatten import flatten, relief_surface
+    rs = np.random.RandomState(8)
+    area, shape = (0, 8000, -1000, 5000), (9, 11)
+    x, y = gridder.regular(area, shape)
+    h = 600 * np.sin(x / 900.) * np.cos(y / 700.) + rs.uniform(-80, 80, x.size)     # crosses ref = 0
+    sets = [0x3FF, 0x008, 0x3F8, 0x3F0, 0x00E, 0x040, 0x100]
+    for variable in (False, True):
+        # dims = (dy, dx) (mesh.py:429)
+        relief = mesher.PrismRelief(0, gridder.spacing(area, shape)[::-1], (x, y, -h))
+        relief.addprop('density', rs.uniform(2000, 3000, x.size) if variable else 2670. * np.ones(x.size))
+        surf = relief_surface(relief)
+        assert surf is not None
+        if not variable:
+            # uniform density: interior reference-plane nodes cancel, the rim stays
+            assert surf.nodes[0].size <= 2 * (shape[0] + 1) + 2 * (shape[1] + 1)
+        flat = flatten(relief, 'density')
+        assert flat.surface is not None
+        grids = [gridder.regular(area, (7, 6), z=-1500.),
+                 gridder.regular((-4e5, 4e5, -4e5, 4e5), (5, 6), z=-3e4),
+                 gridder.regular(area, (9, 11), z=-700.),                 # on the cell centres, above
+                 gridder.scatter(area, 40, z=100., seed=3),                # below some of the tops
+                 (surf.faces[0][:30] + 0.0, surf.faces[2][:30] + 0.0, -900. * np.ones(30))]   # over corners
+        for xp, yp, zp in grids:
+            for m in sets:
+                got, flag = surface_forward(hostsim, m, xp, yp, zp, surf)
+                assert flag == 0
+                fields = [NAMES[i] for i in range(14) if m >> i & 1]
+                for c, fld in enumerate(fields):
+                    ref = oracle.model(fld, xp, yp, zp, flat.bounds, flat.density[:, None], scale=1.0)
+                    cond = oracle.condition(fld, xp, yp, zp, flat.bounds, flat.density[:, None], scale=1.0)
+                    assert_parity(got[c], ref, cond, C_FLOOR_FAST, 'relief surface %s set 0x%x' % (fld, m))
+    # a point IN the reference plane, on a grid line, beyond a node: gxz / gyz raise the flag
+    xp = np.array([surf.nodes[0][0]]); yp = np.array([surf.nodes[1][0] + 7000.]); zp = np.zeros(1)
+    _, flag = surface_forward(hostsim, 0x040, xp, yp, zp, surf)
+    assert flag == 1
+    _, flag = surface_forward(hostsim, 0x008, xp, yp, zp, surf)
+    assert flag == 0
+    # not a tight regular grid: no surface form
+    relief = mesher.PrismRelief(0, (500., 500.), (x, y, -h))
+    relief.addprop('density', 2670. * np.ones(x.size))
+    assert relief_surface(relief) is None
+    xs, ys = gridder.scatter(area, 50, seed=0)
+    relief = mesher.PrismRelief(0, (100., 100.), (xs, ys, -np.ones(50)))
+    relief.addprop('density', 2670. * np.ones(50))
+    assert relief_surface(relief) is None
