@@ -114,6 +114,127 @@ FB_HD void node_accumulate(double (&acc)[popc(MASK)], double X, double Y, double
 }
 
 
+// ---- hot / careful split ---------------------------------------------------------
+// Every special case of the reference (safe_log(0), safe_atan2(0, 0), the shifted r,
+// a root argument below the range of the branch-free root) needs coordinate
+// differences that are zero (or below 2^-480) on TWO axes at once, or a log argument
+// that rounds to zero.  node_eval tests exactly that with exponent compares on the
+// ALU pipe; if ANY lane of the warp has such a node (warp vote: no divergence) the
+// warp takes the out-of-line node_accumulate above, otherwise the straight-line code
+// below, which carries no compares, selects or branches for them.
+FB_HD bool below_2m480(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
+
+// the six per-corner primitives of one node, plus the logs gxy / gxz / gyz use (equal to
+// Lz / Ly / Lx unless the reference shifts r, _prism.pyx:327-330, :359-362, :418-421)
+struct NodePrims {
+    double Lx, Ly, Lz, Axx, Ayy, Azz, Lxy, Lxz, Lyz;
+};
+
+// with every special case of the reference; out of line, rare
+template <uint32_t MASK>
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+static
+#endif
+NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double s0, double s1, double s2)
+{
+    using namespace fm;
+    NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const double ZZ = mul(Z, Z);
+    const double r2 = add(XX_YY, ZZ);
+    double r = root(r2);
+    if (hi32(r2) < 0x03500000) r = sqrt(r2);      // outside the range of the branch-free root
+    if constexpr (MASK & NEED_LX) p.Lx = node_log(add(X, r));
+    if constexpr (MASK & NEED_LY) p.Ly = node_log(add(Y, r));
+    if constexpr (MASK & NEED_LZ) p.Lz = node_log(add(Z, r));
+    if constexpr (MASK & NEED_AXX) p.Axx = node_atan(mul(Z, Y), mul(X, r));
+    if constexpr (MASK & NEED_AYY) p.Ayy = node_atan(mul(Z, X), mul(Y, r));
+    if constexpr (MASK & NEED_AZZ) p.Azz = node_atan(mul(X, Y), mul(Z, r));
+    p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
+    if constexpr (MASK & bit(F_GXY))
+        if (X == 0.0 && Y == 0.0 && Z < 0.0)
+            p.Lxy = safe_log_ref(add(Z, sqrt(add(add(mul(s0, s0), mul(s1, s1)), ZZ))));
+    if constexpr (MASK & bit(F_GXZ))
+        if (X == 0.0 && Z == 0.0 && Y < 0.0)
+            p.Lxz = safe_log_ref(add(Y, sqrt(add(add(mul(s0, s0), mul(s2, s2)), mul(Y, Y)))));
+    if constexpr (MASK & bit(F_GYZ))
+        if (Y == 0.0 && Z == 0.0 && X < 0.0)
+            p.Lyz = safe_log_ref(add(X, sqrt(add(add(mul(s1, s1), mul(s2, s2)), mul(X, X)))));
+    return p;
+}
+
+// tiny_xy = X and Y both below 2^-480; tiny_x_or_y = one of them is (both per node column).
+// The sums below are written with explicit fma / separately rounded products so that a
+// node gives the same bits whichever way its primitives were obtained (the choice is
+// per WARP, and a point must not change its result with its warp-mates: shard invariance).
+template <uint32_t MASK>
+FB_HD void node_eval(double (&acc)[popc(MASK)], double X, double Y, double Z, double XX_YY,
+                     bool tiny_xy, bool tiny_x_or_y, double w0, double w1, double w2,
+                     const double (&f)[3], const double (&sh)[3])
+{
+    using namespace fm;
+    const double ZZ = mul(Z, Z);
+    const double r = root(add(XX_YY, ZZ));
+    double ax = 1.0, ay = 1.0, az = 1.0;
+    bool bad = tiny_xy | (below_2m480(Z) & tiny_x_or_y);
+    // X + r >= +0: zero (or denormal) iff the high word is below the smallest normal's
+    if constexpr (MASK & NEED_LX) { ax = add(X, r); bad = bad | (hi32(ax) < 0x00100000); }
+    if constexpr (MASK & NEED_LY) { ay = add(Y, r); bad = bad | (hi32(ay) < 0x00100000); }
+    if constexpr (MASK & NEED_LZ) { az = add(Z, r); bad = bad | (hi32(az) < 0x00100000); }
+#if defined(__CUDA_ARCH__)
+    bad = __any_sync(0xffffffffu, bad);
+#endif
+    NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (bad) {
+        p = node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2]);
+    } else {
+        if constexpr (MASK & NEED_LX) p.Lx = log_ratio(ax, 1.0);
+        if constexpr (MASK & NEED_LY) p.Ly = log_ratio(ay, 1.0);
+        if constexpr (MASK & NEED_LZ) p.Lz = log_ratio(az, 1.0);
+        if constexpr (MASK & NEED_AXX) p.Axx = atan_ratio(mul(Z, Y), mul(X, r));
+        if constexpr (MASK & NEED_AYY) p.Ayy = atan_ratio(mul(Z, X), mul(Y, r));
+        if constexpr (MASK & NEED_AZZ) p.Azz = atan_ratio(mul(X, Y), mul(Z, r));
+        p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
+    }
+    int c = 0;
+    if constexpr (MASK & bit(F_POT)) {   // _prism.pyx:36-39
+        const double logs = fma(mul(X, Y), p.Lz, fma(mul(Y, Z), p.Lx, mul(mul(X, Z), p.Ly)));
+        const double atans = fma(mul(X, X), p.Axx, fma(mul(Y, Y), p.Ayy, mul(ZZ, p.Azz)));
+        acc[c] = fma(fma(-0.5, atans, logs), w0, acc[c]);
+        ++c;
+    }
+    if constexpr (MASK & bit(F_GX)) {    // :43-44
+        acc[c] = fma(fma(X, p.Axx, -fma(Y, p.Lz, mul(Z, p.Ly))), w0, acc[c]);
+        ++c;
+    }
+    if constexpr (MASK & bit(F_GY)) {    // :46-47
+        acc[c] = fma(fma(Y, p.Ayy, -fma(Z, p.Lx, mul(X, p.Lz))), w0, acc[c]);
+        ++c;
+    }
+    if constexpr (MASK & bit(F_GZ)) {    // :49-50
+        acc[c] = fma(fma(Z, p.Azz, -fma(X, p.Ly, mul(Y, p.Lx))), w0, acc[c]);
+        ++c;
+    }
+    if constexpr (MASK & bit(F_GXX)) { acc[c] = fma(-p.Axx, w0, acc[c]); ++c; }   // :52-53
+    if constexpr (MASK & bit(F_GXY)) { acc[c] = fma(p.Lxy, w0, acc[c]); ++c; }    // :55-56
+    if constexpr (MASK & bit(F_GXZ)) { acc[c] = fma(p.Lxz, w0, acc[c]); ++c; }    // :58-59
+    if constexpr (MASK & bit(F_GYY)) { acc[c] = fma(-p.Ayy, w0, acc[c]); ++c; }   // :61-62
+    if constexpr (MASK & bit(F_GYZ)) { acc[c] = fma(p.Lyz, w0, acc[c]); ++c; }    // :64-65
+    if constexpr (MASK & bit(F_GZZ)) { acc[c] = fma(-p.Azz, w0, acc[c]); ++c; }   // :67-68
+    if constexpr (MASK & MAGNETIC_MASK) {
+        // v1..v6 of _prism.pyx:94-99 at this node (unshifted); w0..w2 = stencils of mx, my, mz
+        const double bx = fma(-p.Axx, w0, fma(p.Lz, w1, mul(p.Ly, w2)));
+        const double by = fma(p.Lz, w0, fma(-p.Ayy, w1, mul(p.Lx, w2)));
+        const double bz = fma(p.Ly, w0, fma(p.Lx, w1, mul(-p.Azz, w2)));
+        if constexpr (MASK & bit(F_TF)) { acc[c] = add(acc[c], fma(f[0], bx, fma(f[1], by, mul(f[2], bz)))); ++c; }
+        if constexpr (MASK & bit(F_BX)) { acc[c] = add(acc[c], bx); ++c; }
+        if constexpr (MASK & bit(F_BY)) { acc[c] = add(acc[c], by); ++c; }
+        if constexpr (MASK & bit(F_BZ)) { acc[c] = add(acc[c], bz); ++c; }
+    }
+    (void)ax; (void)ay; (void)az;
+}
+
 #if defined(__CUDACC__)
 // ---- the kernel ---------------------------------------------------------------
 // thread = observation point, as in prism_forward.cuh.  Nodes are walked with z
@@ -202,6 +323,7 @@ mesh_forward_kernel(const MeshArgs a)
     int a_ = (int)(col - (int64_t)b_ * mv.nxp);
     double X = fm::sub(mv.xn[a_], xp), Y = fm::sub(mv.yn[b_ < mv.nyp ? b_ : mv.nyp - 1], yp);
     double sxy = fm::add(fm::mul(X, X), fm::mul(Y, Y));
+    bool tiny_xy = below_2m480(X) & below_2m480(Y), tiny_x_or_y = below_2m480(X) | below_2m480(Y);
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % FWD_STAGES;
@@ -217,7 +339,7 @@ mesh_forward_kernel(const MeshArgs a)
             const bool live = MAG ? (w0 != 0.0 || w1 != 0.0 || w2 != 0.0) : (w0 != 0.0);
             if (live) {
                 const double Z = fm::sub(z_in_smem ? zn_s[c_] : mv.zn[c_], zp);
-                node_accumulate<MASK>(acc, X, Y, Z, sxy, w0, w1, w2, f, sh);
+                node_eval<MASK>(acc, X, Y, Z, sxy, tiny_xy, tiny_x_or_y, w0, w1, w2, f, sh);
             }
             if (++c_ == mv.nzp) {      // next node column: new X (and Y at the end of a row)
                 c_ = 0;
@@ -228,6 +350,8 @@ mesh_forward_kernel(const MeshArgs a)
                 }
                 X = fm::sub(mv.xn[a_], xp);
                 sxy = fm::add(fm::mul(X, X), fm::mul(Y, Y));
+                tiny_xy = below_2m480(X) & below_2m480(Y);
+                tiny_x_or_y = below_2m480(X) | below_2m480(Y);
             }
         }
         __syncwarp();
