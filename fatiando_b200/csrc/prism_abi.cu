@@ -22,6 +22,7 @@
 #include "prism_masks.h"
 #include "prism_forward.cuh"
 #include "prism_mesh.cuh"
+#include "prism_mesh_jacobian.cuh"
 
 using namespace fb200;
 
@@ -395,7 +396,7 @@ extern "C" int fb200_model_attach_mesh(fb200_model *mod, int nx, int ny, int nz,
     if (!xn || !yn || !zn || !cell_size) return fail(FB200_EINVAL, "NULL mesh array");
     const int nmag = (w_mx != nullptr) + (w_my != nullptr) + (w_mz != nullptr);
     if (nmag != 0 && nmag != 3) return fail(FB200_EINVAL, "w_mx, w_my, w_mz must be all NULL or all given");
-    if (!w_density && nmag == 0) return fail(FB200_EINVAL, "no node weights given");
+    // without node weights the mesh geometry alone is attached: enough for the Jacobian
     std::lock_guard<std::mutex> hold(mod->lock);
     DeviceGuard g(mod->device);
     if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
@@ -900,7 +901,7 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     if (field < 0 || field >= F_COUNT) return fail(FB200_EINVAL, "invalid field id");
     if (!unit_prop) return fail(FB200_EINVAL, "unit_prop is NULL");
     if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
-    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_TRANSPOSED))
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_TRANSPOSED | FB200_PER_CELL))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_jacobian");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
@@ -923,13 +924,61 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     for (int r = 0; r < 3; ++r) a.unit_p[r] = magnetic ? unit_prop[r] : (r == 0 ? unit_prop[0] : 0.0);
     for (int r = 0; r < 3; ++r) a.fvec[r] = fvec ? fvec[r] : 0.0;
     a.scale = scale;
+    // A regular mesh whose prisms are ALL its cells, in mesh order: node-sharing kernel
+    // (prism_mesh_jacobian.cuh), unless the reference order or the per-cell path is asked
+    // for, the node slabs do not fit in shared memory, or a point lies in a hazard wall.
+    bool by_nodes = mod->has_mesh && !exact && !(flags & FB200_PER_CELL) &&
+                    m == (int64_t)(mod->nxp - 1) * (mod->nyp - 1) * (mod->nzp - 1);
+    int mj_points = 8;
+    if (by_nodes) {
+        while (mj_points > 1 && mesh_jacobian_smem(mod->nxp, mod->nzp, mj_points) > (size_t)200 * 1024)
+            mj_points /= 2;
+        if (mesh_jacobian_smem(mod->nxp, mod->nzp, mj_points) > (size_t)200 * 1024) by_nodes = false;
+    }
     auto launch = [&](const JacobianArgs &args) -> cudaError_t {
+        if (by_nodes) {
+            MeshJacArgs ma;
+            std::memset(&ma, 0, sizeof(ma));
+            ma.xn = mod->d_nodes; ma.yn = mod->d_nodes + mod->nxp; ma.zn = mod->d_nodes + mod->nxp + mod->nyp;
+            ma.nxp = mod->nxp; ma.nyp = mod->nyp; ma.nzp = mod->nzp;
+            for (int r = 0; r < 3; ++r) {
+                ma.sh[r] = mod->shift[r]; ma.unit_p[r] = args.unit_p[r]; ma.fvec[r] = args.fvec[r];
+            }
+            ma.xp = args.xp; ma.yp = args.yp; ma.zp = args.zp; ma.n = args.n;
+            ma.scale = args.scale; ma.out = args.out; ma.ld = args.ld;
+            ma.transposed = transposed ? 1 : 0;
+            ma.points = mj_points;
+            return launch_mesh_jacobian(field, ma, mod->stream);
+        }
         return exact ? launch_jacobian_exact(field, transposed, args, mod->stream)
                      : launch_jacobian_fast(field, transposed, args, mod->stream);
+    };
+    auto hazard_hit = [&](const double *dx, const double *dy, const double *dz, int64_t cnt, bool *hit) -> int {
+        *hit = false;
+        if (!(mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2])) return FB200_OK;
+        CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+        const double *coord[3] = {dx, dy, dz};
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!mod->n_hazard[ax]) continue;
+            near_plane_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, mod->stream>>>(
+                coord[ax], cnt, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag);
+            CK(cudaGetLastError());
+        }
+        int raised = 0;
+        CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+        *hit = raised != 0;
+        return FB200_OK;
     };
     // points per launch: grid.y limit, and (host output) a bounded staging block
     const int64_t max_rows_grid = (int64_t)65535 * JAC_TILE;
     if (on_device) {
+        if (by_nodes) {
+            bool hit = false;
+            int rc = hazard_hit(xp, yp, zp, n, &hit);
+            if (rc != FB200_OK) return rc;
+            if (hit) by_nodes = false;
+        }
         CK(cudaEventRecord(mod->ev0, mod->stream));
         for (int64_t r0 = 0; r0 < n; r0 += max_rows_grid) {
             const int64_t rb = std::min(max_rows_grid, n - r0);
@@ -953,6 +1002,12 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     CK(cudaMemcpyAsync(mod->d_pts, xp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     CK(cudaMemcpyAsync(mod->d_pts + 2 * np, zp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
+    if (by_nodes) {
+        bool hit = false;
+        rc = hazard_hit(mod->d_pts, mod->d_pts + np, mod->d_pts + 2 * np, n, &hit);
+        if (rc != FB200_OK) return rc;
+        if (hit) by_nodes = false;
+    }
     int64_t rows = std::max<int64_t>(JAC_TILE, ((int64_t)(256ll << 20) / 8 / m) / JAC_TILE * JAC_TILE);
     rows = std::min(rows, std::min(max_rows_grid, (n + JAC_TILE - 1) / JAC_TILE * JAC_TILE));
     rc = grow(&mod->d_out, &mod->out_cap, (size_t)rows * m, mod->stream);

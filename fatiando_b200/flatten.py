@@ -177,6 +177,27 @@ def _node_weights(values, shape):
     return np.ascontiguousarray(np.transpose(w, (1, 2, 0))).ravel()     # [b][a][c]
 
 
+def mesh_geometry(mesh):
+    """
+    Geometry-only :class:`MeshNodes` (no weights) of a regular ``PrismMesh`` without
+    masked cells -- what the node-sharing Jacobian needs -- or ``None``.
+    """
+    if not _is_prism_mesh(mesh):
+        return None
+    mask = getattr(mesh, 'mask', None)
+    if mask is not None and len(mask):
+        return None
+    nz, ny, nx = (int(v) for v in mesh.shape)
+    dx, dy, dz = (float(d) for d in mesh.dims)
+    if not (dx > 0 and dy > 0 and dz > 0):
+        return None
+    b = mesh.bounds
+    nodes = [_node_coordinates(b[0], dx, nx), _node_coordinates(b[2], dy, ny),
+             _node_coordinates(b[4], dz, nz)]
+    hazard = [_mismatched_walls(c[:-2] + d, c[1:-1]) for c, d in zip(nodes, (dx, dy, dz))]
+    return MeshNodes((nz, ny, nx), nodes[0], nodes[1], nodes[2], (dx, dy, dz), [], hazard)
+
+
 def mesh_nodes(mesh, prop, fvec=None):
     """
     :class:`MeshNodes` of a regular ``PrismMesh`` carrying ``prop`` on every
@@ -324,6 +345,8 @@ def flatten(prisms, prop=None, override=False, fvec=None):
     if prop is not None and not override and index.size:
         nodes = mesh_nodes(prisms, prop, fvec=fvec)
         surface = relief_surface(prisms, prop)
+    elif index.size == total:
+        nodes = mesh_geometry(prisms)          # Jacobian / override models: geometry only
     return FlatModel(bounds, dens, mag, index, total, nodes, surface)
 
 

@@ -149,8 +149,8 @@ class Model(object):
             nd = self.nodes
             nz, ny, nx = nd.shape
             w = nd.weights
-            wd = w[0] if prop == 'density' else None
-            wm = w if prop == 'magnetization' else [None, None, None]
+            wd = w[0] if (prop == 'density' and w) else None
+            wm = w if (prop == 'magnetization' and w) else [None, None, None]
             _lib.check(lib.fb200_model_attach_mesh(
                 self._handle, nx, ny, nz, _lib.dptr(nd.xn), _lib.dptr(nd.yn), _lib.dptr(nd.zn),
                 _lib.dptr(nd.cell_size), _lib.dptr(wd), *[_lib.dptr(c) for c in wm]))
@@ -217,7 +217,7 @@ class Model(object):
         return {_lib.FIELDS[i]: out[c] for c, i in enumerate(ids)}
 
     def jacobian(self, xp, yp, zp, field='gz', pmag=None, fvec=None, transposed=False,
-                 reference_order=False, scaled=True, out=None):
+                 reference_order=False, scaled=True, out=None, per_cell=False):
         """
         Dense sensitivity matrix of ``field`` for unit physical property.
 
@@ -247,6 +247,8 @@ class Model(object):
             flags = self._flags(xp, yp, zp, reference_order)
             if transposed:
                 flags |= _lib.TRANSPOSED
+            if per_cell:
+                flags |= _lib.PER_CELL
             _lib.check(_lib.lib().fb200_jacobian(
                 self._handle, xp.ctypes.data, yp.ctypes.data, zp.ctypes.data, n, fid,
                 _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,

@@ -61,8 +61,8 @@ enum fb200_field {
  * (results are then bit-identical between a full run and any observation
  * shard of it; small problems lose occupancy)                               */
 #define FB200_NO_PRISM_SPLIT   (1u << 3)
-/* forward only: evaluate cell by cell even when a regular mesh is attached
- * (fb200_model_attach_mesh)                                                 */
+/* forward and jacobian: evaluate cell by cell even when a regular mesh or a
+ * relief surface is attached (fb200_model_attach_mesh / _attach_surface)    */
 #define FB200_PER_CELL         (1u << 4)
 
 typedef struct fb200_model fb200_model;
@@ -98,7 +98,11 @@ int fb200_model_create(int device, int64_t m,
  * count as zero).  fb200_forward then evaluates the per-corner kernel once per
  * NODE instead of eight times per cell -- same arithmetic per evaluation,
  * ~2.5-3.5x less of it -- unless a property override, FB200_REFERENCE_ORDER or
- * FB200_PER_CELL is given.  Jacobian and adjoint always work per cell.          */
+ * FB200_PER_CELL is given.  The node weights may all be NULL (geometry only).
+ * fb200_jacobian uses the geometry when the model's prisms are ALL cells of the
+ * mesh in mesh order: every (point, node) kernel value is computed once and
+ * each entry formed as the signed sum of its eight node values.  The adjoint
+ * always works per cell.                                                       */
 int fb200_model_attach_mesh(fb200_model *model, int nx, int ny, int nz,
                             const double *xn, const double *yn, const double *zn,
                             const double *cell_size /* 3 */,

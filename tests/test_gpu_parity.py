@@ -363,6 +363,48 @@ def test_node_sharing_equals_per_cell_and_oracle(gpu_lib, oracle):
     assert_parity(got, ref, cond, C_FLOOR_FAST, 'override on a mesh')
 
 
+def test_node_sharing_jacobian(gpu_lib, oracle):
+    """Jacobian of a whole regular mesh by node sharing against the per-cell kernels and the
+    oracle's per-cell columns: several fields, both layouts, point counts that do not fill a
+    block, a mesh whose node slabs need fewer points per block, points on mesh planes."""
+    from fatiando_b200 import prism, mesher, gridder, utils
+    from fatiando_b200.flatten import flatten
+    cases = [((0, 5000, -300, 4100, 10, 2000), (5, 9, 11), 77),
+             ((0, 4000, 0, 300, 0, 2000), (40, 2, 90), 13)]          # slab 41 x 91: 2 points per block
+    fv = utils.dircos(30, -15)
+    for bounds, shape, npts in cases:
+        mesh = mesher.PrismMesh(bounds, shape)
+        flat = flatten(mesh, None, override=True)
+        assert flat.nodes is not None and not flat.nodes.weights
+        xa, ya, za = gridder.scatter((bounds[0] - 500, bounds[1] + 500, bounds[2] - 500, bounds[3] + 500),
+                                     npts, z=-120., seed=5)
+        # a few points on mesh planes / above mesh nodes
+        xa[:3] = flat.nodes.xn[1]; ya[1:4] = flat.nodes.yn[2]
+        with prism.Model(mesh, None, keep_all=True) as model:
+            for f in ['gz', 'gxx', 'gxy', 'gyz', 'potential', 'tf', 'bz']:
+                pm = list(fv) if f in MAG else None
+                jn = model.jacobian(xa, ya, za, f, pmag=pm, fvec=fv)
+                jc = model.jacobian(xa, ya, za, f, pmag=pm, fvec=fv, per_cell=True)
+                jt = model.jacobian(xa, ya, za, f, pmag=pm, fvec=fv, transposed=True)
+                assert np.array_equal(jt.T, jn), f
+                unit = [1.0] if f not in MAG else (pm + list(fv) if f == 'tf' else pm)
+                ref = oracle.jacobian(f, xa, ya, za, flat.bounds, unit, threads=4)
+                # per-entry floor: the eight corner terms of that cell
+                for q in range(0, flat.size, max(1, flat.size // 40)):
+                    bq = [b[q:q + 1] for b in flat.bounds]
+                    cond = oracle.condition(f, xa, ya, za, bq, np.array([unit], dtype=float))
+                    assert_parity(jn[:, q], ref[:, q], cond, C_FLOOR_FAST, 'node jacobian %s col %d' % (f, q))
+                    assert_parity(jc[:, q], ref[:, q], cond, C_FLOOR_FAST, 'cell jacobian %s col %d' % (f, q))
+                scale = np.abs(ref).max()
+                assert np.max(np.abs(jn - ref)) <= 1e-9 * scale, f
+    # a masked mesh keeps the per-cell kernels (columns scattered back by prism.jacobian)
+    mesh = mesher.PrismMesh((0, 1000, 0, 1000, 0, 500), (2, 3, 4))
+    mesh.mask = [5]
+    assert flatten(mesh, None, override=True).nodes is None
+    j = prism.jacobian(xa, ya, za, mesh, 'gz')
+    assert j.shape == (xa.size, mesh.size) and np.all(j[:, 5] == 0.0)
+
+
 def test_relief_surface_form_equals_per_cell_and_oracle(gpu_lib, oracle):
     """PrismRelief on a tight regular grid: surface form (default) against the per-cell kernels
     and the oracle; the thickness-dependent shift case falls back by itself."""
