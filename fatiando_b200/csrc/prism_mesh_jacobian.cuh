@@ -24,6 +24,7 @@ namespace fb200 {
 
 constexpr int MJ_THREADS = 256;
 constexpr int MJ_WARPS = MJ_THREADS / 32;
+constexpr int MJ_ZPAD = MJ_THREADS + 8;   // z levels the node loop may read past the last one
 
 struct MeshJacArgs {
     const double *xn, *yn, *zn;     // node coordinates
@@ -41,19 +42,23 @@ struct MeshJacArgs {
 };
 
 #if defined(__CUDACC__)
-template <uint32_t MASK>
+template <uint32_t MASK, bool TRANSPOSED>
 __global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJacArgs a)
 {
     static_assert(popc(MASK) == 1, "one field per Jacobian");
     extern __shared__ double sm[];
+    // everything the loops read, once, into registers (not re-fetched from the parameter bank)
     const int P = a.points;
     const int nxp = a.nxp, nzp = a.nzp, nx = nxp - 1, nz = nzp - 1, ny = a.nyp - 1;
     const int slab = nzp * nxp;
+    const double scale = a.scale;
+    const int64_t ld = a.ld;
+    const double *const yn = a.yn;
     double *buf0 = sm, *buf1 = sm + (size_t)P * slab;
     double *xs = buf1 + (size_t)P * slab;          // node x coordinates
     double *zs = xs + nxp;                         // node z coordinates
     for (int i = threadIdx.x; i < nxp; i += MJ_THREADS) xs[i] = a.xn[i];
-    for (int i = threadIdx.x; i < nzp; i += MJ_THREADS) zs[i] = a.zn[i];
+    for (int i = threadIdx.x; i < nzp + MJ_ZPAD; i += MJ_THREADS) zs[i] = a.zn[i < nzp ? i : nzp - 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = warp % P;                        // this warp's point within the block
@@ -65,72 +70,88 @@ __global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJac
     const double f[3] = {a.fvec[0], a.fvec[1], a.fvec[2]};
     const double sh[3] = {a.sh[0], a.sh[1], a.sh[2]};
     const double u0 = a.unit_p[0], u1 = a.unit_p[1], u2 = a.unit_p[2];
+    // C-order: entry (l, col) at out[l*ld + col]; transposed: out[col*ld + l]
+    double *const row_base = TRANSPOSED ? a.out + l : a.out + l * ld;
     __syncthreads();
 
     const int step = 32 * nsub;
     const int rounds = (slab + step - 1) / step;   // same trip count for every lane (warp votes inside)
-    const int cells = nz * nx;
+    const int dq = step / nxp, dr = step - dq * nxp;        // one step in (level, x index) form
+    double *cur = buf0 + (size_t)p * slab, *prev = buf1 + (size_t)p * slab;
+    const int e0 = sub * 32 + lane;
+    const int c0 = e0 / nxp, a0 = e0 - c0 * nxp;
     for (int b = 0; b <= ny; ++b) {
-        double *cur = ((b & 1) ? buf1 : buf0) + (size_t)p * slab;
-        const double *prev = ((b & 1) ? buf0 : buf1) + (size_t)p * slab;
-        const double Y = fm::sub(a.yn[b], py);
+        const double Y = fm::sub(yn[b], py);
         const double YY = fm::mul(Y, Y);
         const bool ty = below_2m480(Y);
         // ---- one kernel evaluation per (point, node) of this row ----
-        int e = sub * 32 + lane;
-        int c = e / nxp, ia = e - c * nxp;
+        // (lanes past the end of the slab keep computing -- the warp votes inside node_eval
+        // need them -- on the padded tail of zs, and do not store)
+        int e = e0, c = c0, ia = a0;
+#pragma unroll 1
         for (int it = 0; it < rounds; ++it) {
-            const bool live = e < slab;
-            const int cc = live ? c : 0, aa = live ? ia : 0;
-            const double X = fm::sub(xs[aa], px), Z = fm::sub(zs[cc], pz);
+            const double X = fm::sub(xs[ia], px), Z = fm::sub(zs[c], pz);
             const bool tx = below_2m480(X);
             double acc[1] = {0.0};
             node_eval<MASK>(acc, X, Y, Z, fm::add(fm::mul(X, X), YY), tx & ty, tx | ty, u0, u1, u2, f, sh);
-            if (live) cur[e] = acc[0];
+            if (e < slab) cur[e] = acc[0];
             e += step;
-            ia += step;
-            while (ia >= nxp) { ia -= nxp; ++c; }
+            ia += dr;
+            c += dq;
+            if (ia >= nxp) { ia -= nxp; ++c; }
         }
         __syncthreads();
-        // ---- the cells between node rows b-1 and b: signed sum of eight node values ----
-        if (b >= 1) {
+        // ---- the cells between node rows b-1 and b ----
+        // lane <-> cell column i, walking down the z levels: d(k) = the x- and y-difference of
+        // the four node columns around the cell at level k, entry(k) = d(k+1) - d(k);
+        // corner (x2, y2, z2) carries +, every lower bound flips the sign (_prism.pyx:104)
+        if (b >= 1 && active) {
             const int j = b - 1;
-            int q = sub * 32 + lane;
-            int k = q / nx, i = q - k * nx;
-            for (; q < cells; q += step) {
-                const int lo = k * nxp + i, hi = lo + nxp;            // z level k, k+1
-                // corner (x2, y2, z2) carries +, every lower bound flips the sign (_prism.pyx:104)
-                const double top = (cur[hi + 1] - cur[hi]) - (prev[hi + 1] - prev[hi]);
-                const double bot = (cur[lo + 1] - cur[lo]) - (prev[lo + 1] - prev[lo]);
-                const double v = (top - bot) * a.scale;
-                const int64_t col = ((int64_t)k * ny + j) * nx + i;
-                if (active) {
-                    if (a.transposed) __stcs(a.out + col * a.ld + l, v);
-                    else __stcs(a.out + l * a.ld + col, v);
+            const int64_t kstride = (int64_t)ny * nx * (TRANSPOSED ? ld : 1);
+            for (int i = sub * 32 + lane; i < nx; i += step) {
+                const double *cp = cur + i, *pp = prev + i;
+                double *dst = TRANSPOSED ? row_base + ((int64_t)j * nx + i) * ld
+                                         : row_base + ((int64_t)j * nx + i);
+                double below = (cp[1] - cp[0]) - (pp[1] - pp[0]);
+#pragma unroll 4
+                for (int k = 0; k < nz; ++k) {
+                    cp += nxp;
+                    pp += nxp;
+                    const double above = (cp[1] - cp[0]) - (pp[1] - pp[0]);
+                    __stcs(dst, (above - below) * scale);
+                    dst += kstride;
+                    below = above;
                 }
-                i += step;
-                while (i >= nx) { i -= nx; ++k; }
             }
         }
         __syncthreads();
+        double *t = cur; cur = prev; prev = t;
     }
 }
 
 // shared memory the kernel needs for P points per block
 inline size_t mesh_jacobian_smem(int nxp, int nzp, int P)
 {
-    return ((size_t)2 * P * nxp * nzp + nxp + nzp) * sizeof(double);
+    return ((size_t)2 * P * nxp * nzp + nxp + nzp + MJ_ZPAD) * sizeof(double);
 }
 
 template <uint32_t MASK>
 inline cudaError_t launch_mesh_jacobian_t(const MeshJacArgs &a, cudaStream_t stream)
 {
     const size_t smem = mesh_jacobian_smem(a.nxp, a.nzp, a.points);
-    cudaError_t e = cudaFuncSetAttribute(mesh_jacobian_kernel<MASK>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const unsigned blocks = (unsigned)((a.n + a.points - 1) / a.points);
-    mesh_jacobian_kernel<MASK><<<blocks, MJ_THREADS, smem, stream>>>(a);
+    cudaError_t e;
+    if (a.transposed) {
+        e = cudaFuncSetAttribute(mesh_jacobian_kernel<MASK, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mesh_jacobian_kernel<MASK, true><<<blocks, MJ_THREADS, smem, stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(mesh_jacobian_kernel<MASK, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mesh_jacobian_kernel<MASK, false><<<blocks, MJ_THREADS, smem, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 #endif  // __CUDACC__

@@ -31,7 +31,7 @@ def main():
         for _ in range(reps):
             t0 = time.perf_counter()
             if w['kind'] == 'jacobian':
-                rows = min(w['xp'].size, 2048)
+                rows = min(w['xp'].size, int(sys.argv[sys.argv.index('--rows') + 1]) if '--rows' in sys.argv else 2048)
                 model.jacobian(w['xp'][:rows], w['yp'][:rows], w['zp'][:rows], w['names'][0],
                                reference_order=exact)
                 pairs = rows * model.size
