@@ -69,7 +69,8 @@ EXECUTED_FP64_PER_PAIR = {"c2": 432.0, "c2a": 432.0, "c3": 441.8, "c4": 318.5, "
                           "c5full": 318.5, "c5tfull": 523.3, "c4full": 318.5}   # profiles/r01_*
 # the same for the node-sharing kernel of regular meshes, per CELL x point pair
 # (profiles/r01_c2_tensor_nodes.txt, r01_c3_mag4_nodes.txt)
-EXECUTED_FP64_PER_PAIR_NODES = {"c2": 221.2, "c2a": 221.2, "c3": 231.7}
+EXECUTED_FP64_PER_PAIR_NODES = {"c2": 193.9, "c2a": 193.9, "c3": 231.7,
+                                "c4": 112.9, "c4full": 112.9}      # c4: profiles/r01_c4_jacobian_nodes.txt
 # and for the surface form of a relief (profiles/r01_c5_gz_surface.txt, r01_c5t_gz_tensor_surface.txt)
 EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 208.6, "c5t": 353.7, "c5full": 208.6, "c5tfull": 353.7}
 
@@ -419,7 +420,7 @@ def run_gpu(args):
         per_gpu = value / world
         achieved = per_gpu * wk['flop'] / 1e12
         peak = sustained.value if ms_per_step > 500 else burst.value
-        executed = (EXECUTED_FP64_PER_PAIR_NODES if model.nodes is not None and w['kind'] == 'forward'
+        executed = (EXECUTED_FP64_PER_PAIR_NODES if model.nodes is not None
                     else EXECUTED_FP64_PER_PAIR_SURFACE if model.surface is not None and w['kind'] == 'forward'
                     else EXECUTED_FP64_PER_PAIR).get(args.workload)
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
@@ -456,6 +457,9 @@ def run_gpu(args):
                            "fields": names, "parallelism": "obs-shard x%d" % world,
                            "evaluation": ("node-sharing (regular mesh: one kernel evaluation per node)"
                                           if model.nodes is not None and w['kind'] == 'forward' else
+                                          "node-sharing Jacobian (one kernel evaluation per point and node, "
+                                          "entries = signed sums of eight node values)"
+                                          if model.nodes is not None else
                                           "surface form (relief: top faces + merged reference-plane nodes)"
                                           if model.surface is not None and w['kind'] == 'forward' else
                                           "per cell"),
