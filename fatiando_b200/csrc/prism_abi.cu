@@ -91,6 +91,7 @@ struct fb200_model {
     double *d_face[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x1 x2 y1 y2 zf zo w
     double *d_snode[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // xn shx yn shy zn zn w
     int *d_flag = nullptr;
+    double *d_adj = nullptr; size_t adj_cap = 0;       // node-sharing adjoint: point rows, node list, V
     // cell walls whose coordinate the reference computes differently from the two sides
     // (x2 of one cell != x1 of the next, one ulp apart): see fb200_model_set_hazard_planes
     double *d_hazard[3] = {nullptr, nullptr, nullptr};
@@ -209,6 +210,55 @@ __global__ void near_plane_kernel(const double *c, int64_t n, const double *plan
     if (near) *flag = 1;
 }
 
+// ---- node-sharing adjoint helpers (fb200_adjoint) ------------------------------
+// rows[r][l]: xpt, shx, ypt, shy, zpt, shz, data*u0 [, data*u1, data*u2]; padding = zero weight
+__global__ void adjoint_rows_kernel(const double *xp, const double *yp, const double *zp,
+                                    const double *data, int64_t n, int64_t n_pad, int nw, double u0,
+                                    double u1, double u2, double shx, double shy, double shz,
+                                    double *rows)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_pad) return;
+    const bool in = l < n;
+    const int64_t s = in ? l : n - 1;
+    const double d = in ? data[s] : 0.0;
+    rows[l] = xp[s];             rows[n_pad + l] = shx;
+    rows[2 * n_pad + l] = yp[s]; rows[3 * n_pad + l] = shy;
+    rows[4 * n_pad + l] = zp[s]; rows[5 * n_pad + l] = shz;
+    rows[6 * n_pad + l] = d * u0;
+    if (nw == 3) { rows[7 * n_pad + l] = d * u1; rows[8 * n_pad + l] = d * u2; }
+}
+
+// node id = (b*nxp + a)*nzp + c  ->  its coordinates
+__global__ void expand_nodes_kernel(const double *xn, const double *yn, const double *zn, int nxp,
+                                    int nyp, int nzp, int64_t nn_pad, double *out)
+{
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nn = (int64_t)nxp * nyp * nzp;
+    if (id >= nn) return;
+    const int c = (int)(id % nzp);
+    const int64_t col = id / nzp;
+    const int a = (int)(col % nxp), b = (int)(col / nxp);
+    out[id] = xn[a]; out[nn_pad + id] = yn[b]; out[2 * nn_pad + id] = zn[c];
+}
+
+// J^T d of cell q = signed sum of V over its eight corners; corner (x2, y2, z2) carries +,
+// every lower bound flips the sign (_prism.pyx:104)
+__global__ void adjoint_cells_kernel(const double *V, int nx, int ny, int nz, double scale, double *out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = (int64_t)nx * ny * nz;
+    if (q >= m) return;
+    const int i = (int)(q % nx);
+    const int64_t rest = q / nx;
+    const int j = (int)(rest % ny), k = (int)(rest / ny);
+    const int nxp = nx + 1, nzp = nz + 1;
+    auto v = [&](int a, int b, int c) { return V[((int64_t)b * nxp + a) * nzp + c]; };
+    const double top = (v(i + 1, j + 1, k + 1) - v(i, j + 1, k + 1)) - (v(i + 1, j, k + 1) - v(i, j, k + 1));
+    const double bot = (v(i + 1, j + 1, k) - v(i, j + 1, k)) - (v(i + 1, j, k) - v(i, j, k));
+    out[q] = (top - bot) * scale;
+}
+
 __global__ void fill_kernel(double *p, int64_t n, double v)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +368,7 @@ extern "C" int fb200_model_destroy(fb200_model *model)
     for (int r = 0; r < 7; ++r)
         if (model->d_snode[r] && r != 5) cudaFreeAsync(model->d_snode[r], st);   // row 5 aliases row 4
     if (model->d_flag) cudaFreeAsync(model->d_flag, st);
+    if (model->d_adj) cudaFreeAsync(model->d_adj, st);
     for (double *p : model->d_hazard) if (p) cudaFreeAsync(p, st);
     StreamSet set;
     set.stream = model->stream; set.ev0 = model->ev0; set.ev1 = model->ev1;
@@ -1051,7 +1102,7 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
     if (field < 0 || field >= F_COUNT) return fail(FB200_EINVAL, "invalid field id");
     if (!unit_prop) return fail(FB200_EINVAL, "unit_prop is NULL");
     if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
-    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER))
+    if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_PER_CELL))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_adjoint");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
@@ -1084,9 +1135,75 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         d_xp = mod->d_pts; d_yp = mod->d_pts + np; d_zp = mod->d_pts + 2 * np; d_w = mod->d_pts + 3 * np;
         d_out = mod->d_out;
     }
+    // whole regular mesh in mesh order: node sharing (EvalNodeRev), unless a point lies in a
+    // hazard wall (fb200_model_set_hazard_planes)
+    bool by_nodes = n > 0 && mod->has_mesh && !exact && !(flags & FB200_PER_CELL) &&
+                    m == (int64_t)(mod->nxp - 1) * (mod->nyp - 1) * (mod->nzp - 1);
+    if (by_nodes && (mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2])) {
+        CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+        const double *coord[3] = {d_xp, d_yp, d_zp};
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!mod->n_hazard[ax]) continue;
+            near_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(
+                coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag);
+            CK(cudaGetLastError());
+        }
+        int raised = 0;
+        CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+        if (raised) by_nodes = false;
+    }
     if (n == 0) {
         fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, mod->stream>>>(d_out, m, 0.0);
         CK(cudaGetLastError());
+    } else if (by_nodes) {
+        const int nw = magnetic ? 3 : 1;
+        const int64_t n_pad = (n + TILE - 1) / TILE * TILE;
+        const int64_t nn = mod->nnodes, nn_pad = (nn + 31) / 32 * 32;
+        // scratch: point rows | node coordinates | V
+        const size_t need = (size_t)(6 + nw) * n_pad + (size_t)4 * nn_pad;
+        int rc = grow(&mod->d_adj, &mod->adj_cap, need, mod->stream);
+        if (rc != FB200_OK) return rc;
+        double *rows = mod->d_adj, *nodes = rows + (size_t)(6 + nw) * n_pad, *V = nodes + (size_t)3 * nn_pad;
+        CK(cudaEventRecord(mod->ev0, mod->stream));
+        adjoint_rows_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, mod->stream>>>(
+            d_xp, d_yp, d_zp, d_w, n, n_pad, nw, unit_prop[0], magnetic ? unit_prop[1] : 0.0,
+            magnetic ? unit_prop[2] : 0.0, mod->shift[0], mod->shift[1], mod->shift[2], rows);
+        CK(cudaGetLastError());
+        expand_nodes_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, mod->stream>>>(
+            mod->d_nodes, mod->d_nodes + mod->nxp, mod->d_nodes + mod->nxp + mod->nyp, mod->nxp,
+            mod->nyp, mod->nzp, nn_pad, nodes);
+        CK(cudaGetLastError());
+        ForwardArgs a;
+        std::memset(&a, 0, sizeof(a));
+        for (int r = 0; r < 6; ++r) a.model.b[r] = rows + (size_t)r * n_pad;
+        for (int r = 0; r < nw; ++r) a.model.p[r] = rows + (size_t)(6 + r) * n_pad;
+        a.model.m = n;
+        a.xp = nodes; a.yp = nodes + nn_pad; a.zp = nodes + 2 * nn_pad; a.n = nn;
+        for (int r = 0; r < 3; ++r) a.fvec[r] = fvec ? fvec[r] : 0.0;
+        const int64_t blocks_x = (nn + FWD_THREADS - 1) / FWD_THREADS;
+        const int64_t tiles = n_pad / TILE;
+        int64_t nsplit = std::min<int64_t>(
+            std::max<int64_t>(1, ((int64_t)mod->sm_count * 20 + blocks_x - 1) / blocks_x), tiles);
+        nsplit = std::min<int64_t>(nsplit, 32000);
+        const int64_t chunk = ((tiles + nsplit - 1) / nsplit) * TILE;
+        nsplit = (n + chunk - 1) / chunk;
+        rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * nn_pad, mod->stream);
+        if (rc != FB200_OK) return rc;
+        a.chunk = chunk;
+        a.nsplit = (int)std::max<int64_t>(nsplit, 2);     // partial-sum output mode
+        a.out = mod->d_part;
+        a.ld = nn_pad;
+        CK(launch_forward_node_rev(field, a, (int)nsplit, mod->stream));
+        const double one[1] = {1.0};
+        const int row0[1] = {0};
+        rc = reduce_split(mod, 1, nsplit, nn, nn_pad, one, row0, V, nn_pad);
+        if (rc != FB200_OK) return rc;
+        adjoint_cells_kernel<<<(unsigned)((m + 255) / 256), 256, 0, mod->stream>>>(
+            V, mod->nxp - 1, mod->nyp - 1, mod->nzp - 1, scale, d_out);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(mod->ev1, mod->stream));
+        mod->last_launches = 5;
     } else {
         // split the points so that every SM has work even for small models
         const int64_t blocks_x = (m + JAC_THREADS - 1) / JAC_THREADS;

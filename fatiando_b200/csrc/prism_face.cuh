@@ -328,4 +328,24 @@ struct EvalNode {
     }
 };
 
+// The adjoint of a regular mesh by node sharing: the thread is a mesh NODE, the staged
+// rows are observation points with weights w = data[l] * unit property,
+//     V(node) = sum_l K(node - point_l) * w_l,
+// and J^T d of a cell is the signed sum of V over its eight corners (prism_abi.cu).
+// Rows: xpt, shx, ypt, shy, zpt, shz, w0 [, w1, w2]   (sh = 1e-5 * cell size).
+struct EvalNodeRev {
+    static constexpr bool NEEDS_FLAG = false;
+    template <uint32_t MASK>
+    static FB_HD_M void pair(double (&acc)[popc(MASK)], double xn, double yn, double zn,
+                           double xpt, double shx, double ypt, double shy, double zpt, double shz,
+                           double w0, double w1, double w2, const double (&f)[3])
+    {
+        using namespace fm;
+        const double X = add(sub(xn, xpt), 0.0), Y = add(sub(yn, ypt), 0.0), Z = add(sub(zn, zpt), 0.0);
+        const double sh[3] = {shx, shy, shz};
+        const bool tx = below_2m480(X), ty = below_2m480(Y);
+        node_eval<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), tx & ty, tx | ty, w0, w1, w2, f, sh);
+    }
+};
+
 }  // namespace fb200

@@ -21,6 +21,7 @@ cudaError_t launch_adjoint_fast(int field, const AdjointArgs &a, int nsplit, cud
 
 cudaError_t launch_forward_face(uint32_t mask, const ForwardArgs &a, int grid_y, cudaStream_t s);   // fwd_surface.cu
 cudaError_t launch_forward_node(uint32_t mask, const ForwardArgs &a, int grid_y, cudaStream_t s);   // fwd_surface.cu
+cudaError_t launch_forward_node_rev(int field, const ForwardArgs &a, int grid_y, cudaStream_t s);    // fwd_surface.cu
 cudaError_t launch_mesh_forward(uint32_t mask, const MeshArgs &a, cudaStream_t s);               // fwd_mesh.cu
 cudaError_t launch_mesh_jacobian(int field, const MeshJacArgs &a, cudaStream_t s);              // fwd_mesh.cu
 

@@ -256,7 +256,7 @@ class Model(object):
         return out
 
     def adjoint(self, xp, yp, zp, data, field='gz', pmag=None, fvec=None,
-                reference_order=False, scaled=True):
+                reference_order=False, scaled=True, per_cell=False):
         """
         ``J.T @ data`` without building ``J``: for every prism q, the sum over
         the points of ``data[l]`` times the unit-property effect of q at l
@@ -281,7 +281,8 @@ class Model(object):
             _lib.check(_lib.lib().fb200_adjoint(
                 self._handle, xp.ctypes.data, yp.ctypes.data, zp.ctypes.data, xp.size, fid,
                 _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
-                data.ctypes.data, out.ctypes.data, self._flags(xp, yp, zp, reference_order)))
+                data.ctypes.data, out.ctypes.data,
+                self._flags(xp, yp, zp, reference_order) | (_lib.PER_CELL if per_cell else 0)))
         return out
 
     def last_kernel_ms(self):

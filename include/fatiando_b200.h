@@ -101,8 +101,8 @@ int fb200_model_create(int device, int64_t m,
  * FB200_PER_CELL is given.  The node weights may all be NULL (geometry only).
  * fb200_jacobian uses the geometry when the model's prisms are ALL cells of the
  * mesh in mesh order: every (point, node) kernel value is computed once and
- * each entry formed as the signed sum of its eight node values.  The adjoint
- * always works per cell.                                                       */
+ * each entry formed as the signed sum of its eight node values; fb200_adjoint
+ * accumulates per NODE and differences the node sums into cells.              */
 int fb200_model_attach_mesh(fb200_model *model, int nx, int ny, int nz,
                             const double *xn, const double *yn, const double *zn,
                             const double *cell_size /* 3 */,

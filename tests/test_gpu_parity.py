@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
-from helpers import (GRAV, MAG, KERN, C_FLOOR_FAST, C_FLOOR_EXACT, assert_parity, golden_model,
+from helpers import (GRAV, MAG, KERN, C_FLOOR_FAST, C_FLOOR_EXACT, EPS, assert_parity, golden_model,
                      prisms_from_golden)
 
 pytestmark = pytest.mark.gpu
@@ -533,7 +533,7 @@ def test_single_process_multi_device(gpu_lib):
 def test_adjoint_is_the_transposed_jacobian(gpu_lib, oracle):
     """J^T d on the fly (imaging.py:116-118): against the reference's stored columns,
     and <J p, d> = <p, J^T d> at a size where J is never formed."""
-    from fatiando_b200 import prism, mesher, gridder
+    from fatiando_b200 import prism, mesher, gridder, utils
     d = load_golden("jacobian")
     mesh = mesher.PrismMesh(tuple(d['mesh_bounds']), tuple(int(v) for v in d['mesh_shape']))
     xp, yp, zp = d['xp'], d['yp'], d['zp']
@@ -564,3 +564,24 @@ def test_adjoint_is_the_transposed_jacobian(gpu_lib, oracle):
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
     again = prism.adjoint(xp, yp, zp, mesh, data, 'gz')
     assert np.array_equal(again, prism.adjoint(xp, yp, zp, mesh, data, 'gz'))   # reproducible
+    # the whole-mesh adjoint runs by node sharing: against the per-cell kernels and, on a sample
+    # of cells, against the oracle's columns with the floor of the summands it adds up
+    # (eps * sum_l |d_l| * A_lq, A = the eight corner terms of cell q at point l)
+    from fatiando_b200.flatten import flatten
+    fv = utils.dircos(30, -15)
+    flat = flatten(mesh, None, override=True)
+    sample = list(range(0, flat.size, flat.size // 24))
+    with prism.Model(mesh, None, keep_all=True) as model:
+        assert model.nodes is not None
+        for f in ['gz', 'gxy', 'gzz', 'tf']:
+            pm = list(fv) if f == 'tf' else None
+            unit = [1.0] if pm is None else pm + list(fv)
+            a = model.adjoint(xp, yp, zp, data, f, pmag=pm, fvec=fv)
+            b = model.adjoint(xp, yp, zp, data, f, pmag=pm, fvec=fv, per_cell=True)
+            for q in sample:
+                bq = [v[q:q + 1] for v in flat.bounds]
+                col = oracle.jacobian(f, xp, yp, zp, bq, unit, threads=4)[:, 0]
+                cond = oracle.condition(f, xp, yp, zp, bq, np.array([unit], dtype=float), threads=4)
+                want, floor = float(col @ data), C_FLOOR_FAST * EPS * float(cond @ np.abs(data))
+                assert abs(a[q] - want) <= 1e-9 * abs(want) + floor, (f, q, 'nodes')
+                assert abs(b[q] - want) <= 1e-9 * abs(want) + floor, (f, q, 'cells')
