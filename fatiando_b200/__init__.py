@@ -11,6 +11,9 @@ kernel ``_prism``, the prism meshes that feed it, and the dense sensitivity
 * :mod:`fatiando_b200.mesher`  -- ``Prism``, ``PrismMesh``, ``PrismRelief``
 * :mod:`fatiando_b200.flatten` -- mesh -> SoA arrays
 * :mod:`fatiando_b200.partition` -- observation / prism sharding over GPUs
+* :mod:`fatiando_b200.harvester` -- drop-in for ``fatiando.gravmag.harvester`` (planting
+  inversion) on a device-resident effect engine
+* :mod:`fatiando_b200.sphere`  -- drop-in for ``fatiando.gravmag.sphere`` (sibling kernel)
 * :mod:`fatiando_b200.gridder`, :mod:`~fatiando_b200.utils`,
   :mod:`~fatiando_b200.constants` -- the support functions the path uses
 
@@ -20,6 +23,7 @@ implementation behind it.
 """
 from . import constants, gridder, mesher, utils          # noqa: F401
 from . import flatten, prism, _prism, partition          # noqa: F401
-from .mesher import Prism, PrismMesh, PrismRelief        # noqa: F401
+from . import harvester, sphere                          # noqa: F401
+from .mesher import Prism, PrismMesh, PrismRelief, Sphere    # noqa: F401
 
 __version__ = "0.1.0"

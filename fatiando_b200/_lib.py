@@ -36,6 +36,8 @@ _SIGNATURES = {
                            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i64)], ctypes.c_int),
     "fb200_model_create": ([ctypes.c_int, _i64] + [_dp] * 10 + [ctypes.POINTER(ctypes.c_void_p)],
                            ctypes.c_int),
+    "fb200_model_create_spheres": ([ctypes.c_int, _i64] + [_dp] * 8 + [ctypes.POINTER(ctypes.c_void_p)],
+                                   ctypes.c_int),
     "fb200_model_attach_mesh": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
                                 + [_dp] * 8, ctypes.c_int),
     "fb200_model_attach_surface": ([ctypes.c_void_p, _i64] + [_dp] * 7 + [_i64] + [_dp] * 5,

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -23,6 +24,7 @@
 #include "prism_forward.cuh"
 #include "prism_mesh.cuh"
 #include "prism_mesh_jacobian.cuh"
+#include "sphere.cuh"
 
 using namespace fb200;
 
@@ -67,6 +69,7 @@ struct DeviceGuard {
 struct fb200_model {
     int device = 0;
     int sm_count = 148;
+    bool spheres = false;        // rows hold spheres (sphere.cuh), not prisms
     int64_t m = 0;
     double *d_b[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_dens = nullptr;
@@ -437,6 +440,23 @@ extern "C" int fb200_model_create(int device, int64_t m, const double *x1, const
     return FB200_OK;
 }
 
+extern "C" int fb200_model_create_spheres(int device, int64_t m, const double *xc, const double *yc,
+                                          const double *zc, const double *radius,
+                                          const double *density, const double *mx,
+                                          const double *my, const double *mz, fb200_model **out)
+{
+    if (m < 0 || (m > 0 && (!xc || !yc || !zc || !radius)))
+        return fail(FB200_EINVAL, "fb200_model_create_spheres: NULL array or negative size");
+    // volume = 4*pi*radius**3/3 with the reference's association (sphere.py:348)
+    std::vector<double> vol((size_t)m), zero((size_t)m, 0.0);
+    for (int64_t q = 0; q < m; ++q) vol[(size_t)q] = 4 * 3.141592653589793 * std::pow(radius[q], 3.0) / 3;
+    int rc = fb200_model_create(device, m, xc, vol.data(), yc, zero.data(), zc, zero.data(), density,
+                                mx, my, mz, out);
+    if (rc != FB200_OK) return rc;
+    (*out)->spheres = true;
+    return FB200_OK;
+}
+
 extern "C" int fb200_model_attach_mesh(fb200_model *mod, int nx, int ny, int nz, const double *xn,
                                        const double *yn, const double *zn,
                                        const double *cell_size, const double *w_density,
@@ -570,6 +590,8 @@ static const uint32_t kGravitySets[] = {
     FB200_GRAVITY_SETS(X)
 #undef X
 };
+// spheres: gz and the tensor only (sphere.cuh)
+static const uint32_t kSphereGravitySets[] = {0x008, 0x010, 0x020, 0x040, 0x080, 0x100, 0x200, 0x3F0, 0x3F8};
 static const uint32_t kMagneticSets[] = {
 #define X(M) (M),
     FB200_MAGNETIC_SETS(X)
@@ -774,6 +796,7 @@ static int run_set(fb200_model *mod, uint32_t set, uint32_t request, bool exact,
     a.chunk = chunk;
     a.nsplit = (int)nsplit;
     auto launch = [&](const ForwardArgs &args) -> cudaError_t {
+        if (mod->spheres) return launch_forward_sphere(set, args, mod->stream);
         if (exact) return launch_forward_exact(set, args, mod->stream);
         return magnetic ? launch_forward_fast_mag(set, args, mod->stream)
                         : launch_forward_fast_grav(set, args, mod->stream);
@@ -817,6 +840,9 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         return fail(FB200_EPROP, "magnetic field requested but the model holds no magnetization");
     if ((mmask & bit(F_TF)) && !fvec)
         return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
+    if (mod->spheres && (field_mask & ~SPHERE_FIELDS))
+        return fail(FB200_EUNSUP, "spheres offer gz, gxx..gzz, tf, bx, by, bz only (sphere.py)");
+    if (mod->spheres && init) return fail(FB200_EUNSUP, "no accumulate entry points for spheres");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
     const bool split = !exact && !(flags & FB200_NO_PRISM_SPLIT);
@@ -885,7 +911,7 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
             if (surface) CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
             if (gmask) {
                 const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
-                for (uint32_t set : cover(gmask, kGravitySets)) {
+                for (uint32_t set : mod->spheres ? cover(gmask, kSphereGravitySets) : cover(gmask, kGravitySets)) {
                     int rc = surface
                         ? run_set_surface(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, scale, d_out, ld)
                         : use_nodes
@@ -954,6 +980,8 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
     if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_TRANSPOSED | FB200_PER_CELL))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_jacobian");
+    if (mod->spheres && !((SPHERE_FIELDS >> field) & 1u))
+        return fail(FB200_EUNSUP, "spheres offer gz, gxx..gzz, tf, bx, by, bz only (sphere.py)");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
     const bool transposed = (flags & FB200_TRANSPOSED) != 0;
@@ -1001,6 +1029,7 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
             ma.points = mj_points;
             return launch_mesh_jacobian(field, ma, mod->stream);
         }
+        if (mod->spheres) return launch_jacobian_sphere(field, transposed, args, mod->stream);
         return exact ? launch_jacobian_exact(field, transposed, args, mod->stream)
                      : launch_jacobian_fast(field, transposed, args, mod->stream);
     };
@@ -1104,6 +1133,7 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
     if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
     if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_PER_CELL))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_adjoint");
+    if (mod->spheres) return fail(FB200_EUNSUP, "fb200_adjoint is not offered for spheres");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
     const int64_t m = mod->m;

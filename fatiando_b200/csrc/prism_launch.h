@@ -19,6 +19,8 @@ cudaError_t launch_jacobian_fast(int field, bool transposed, const JacobianArgs 
 cudaError_t launch_adjoint_exact(int field, const AdjointArgs &a, int nsplit, cudaStream_t s);   // jac_exact.cu
 cudaError_t launch_adjoint_fast(int field, const AdjointArgs &a, int nsplit, cudaStream_t s);    // jac_fast.cu
 
+cudaError_t launch_forward_sphere(uint32_t mask, const ForwardArgs &a, cudaStream_t s);                  // fwd_sphere.cu
+cudaError_t launch_jacobian_sphere(int field, bool transposed, const JacobianArgs &a, cudaStream_t s);  // fwd_sphere.cu
 cudaError_t launch_forward_face(uint32_t mask, const ForwardArgs &a, int grid_y, cudaStream_t s);   // fwd_surface.cu
 cudaError_t launch_forward_node(uint32_t mask, const ForwardArgs &a, int grid_y, cudaStream_t s);   // fwd_surface.cu
 cudaError_t launch_forward_node_rev(int field, const ForwardArgs &a, int grid_y, cudaStream_t s);    // fwd_surface.cu

@@ -60,6 +60,41 @@ class Prism(object):
         return ' | '.join('%s:%g' % (k, v) for k, v in items)
 
 
+class Sphere(object):
+    """
+    A sphere.  x -> North, y -> East, z -> Down.
+
+    * x, y, z : coordinates of the centre
+    * radius : radius of the sphere
+    * props : dict of physical properties, e.g.
+      ``{'density': 2670, 'magnetization': [mx, my, mz]}``
+
+    >>> s = Sphere(1, 2, 3, 10, {'magnetization': 200})
+    >>> s.props['magnetization']
+    200
+    >>> s.addprop('density', 20)
+    >>> print(s)
+    x:1 | y:2 | z:3 | radius:10 | density:20 | magnetization:200
+    """
+
+    def __init__(self, x, y, z, radius, props=None):
+        self.props = props if props is not None else {}
+        self.x, self.y, self.z = float(x), float(y), float(z)
+        self.radius = float(radius)
+        self.center = np.array([x, y, z])
+
+    def addprop(self, prop, value):
+        self.props[prop] = value
+
+    def copy(self):
+        return Sphere(self.x, self.y, self.z, self.radius, props=dict(self.props))
+
+    def __str__(self):
+        names = [('x', self.x), ('y', self.y), ('z', self.z), ('radius', self.radius)]
+        names.extend((p, self.props[p]) for p in sorted(self.props))
+        return ' | '.join('%s:%g' % (n, v) for n, v in names)
+
+
 class _PrismSequence(object):
     """Iteration protocol shared by the two meshes (py2 ``next`` kept too)."""
 

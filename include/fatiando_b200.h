@@ -89,6 +89,18 @@ int fb200_model_create(int device, int64_t m,
                        const double *density,
                        const double *mx, const double *my, const double *mz,
                        fb200_model **out);
+/* Sibling model family: spheres (fatiando/gravmag/sphere.py:45-746).  Sphere q has
+ * centre (xc, yc, zc), `radius`, and density and/or magnetization like a prism.
+ * The handle works with fb200_forward and fb200_jacobian for the fields
+ * sphere.py offers -- FB200_GZ, FB200_GXX..FB200_GZZ, FB200_TF, FB200_BX/BY/BZ
+ * (anything else: FB200_EUNSUP) -- with the same overrides, unit factors,
+ * layouts and flags; FB200_REFERENCE_ORDER is accepted and changes nothing
+ * (there is one evaluator, in the reference's operation order).              */
+int fb200_model_create_spheres(int device, int64_t m,
+                               const double *xc, const double *yc, const double *zc,
+                               const double *radius, const double *density,
+                               const double *mx, const double *my, const double *mz,
+                               fb200_model **out);
 /* Regular-mesh acceleration (optional).  Declares that the model's prisms are
  * the unmasked cells of a regular nx*ny*nz PrismMesh (mesh.py:495-665) and hands
  * over its node-sharing form: node coordinates xn[nx+1], yn[ny+1], zn[nz+1]
