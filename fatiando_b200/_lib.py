@@ -38,6 +38,8 @@ _SIGNATURES = {
                            ctypes.c_int),
     "fb200_model_create_spheres": ([ctypes.c_int, _i64] + [_dp] * 8 + [ctypes.POINTER(ctypes.c_void_p)],
                                    ctypes.c_int),
+    "fb200_model_create_polyprisms": ([ctypes.c_int, _i64, ctypes.POINTER(_i64)] + [_dp] * 8
+                                      + [ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
     "fb200_model_attach_mesh": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
                                 + [_dp] * 8, ctypes.c_int),
     "fb200_model_attach_surface": ([ctypes.c_void_p, _i64] + [_dp] * 7 + [_i64] + [_dp] * 5,

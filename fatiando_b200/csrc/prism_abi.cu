@@ -70,6 +70,7 @@ struct fb200_model {
     int device = 0;
     int sm_count = 148;
     bool spheres = false;        // rows hold spheres (sphere.cuh), not prisms
+    bool poly_edges = false;     // rows hold polygon edges (polyprism.cuh)
     int64_t m = 0;
     double *d_b[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_dens = nullptr;
@@ -457,6 +458,40 @@ extern "C" int fb200_model_create_spheres(int device, int64_t m, const double *x
     return FB200_OK;
 }
 
+extern "C" int fb200_model_create_polyprisms(int device, int64_t nprisms, const int64_t *first_vertex,
+                                             const double *vx, const double *vy, const double *z1,
+                                             const double *z2, const double *density,
+                                             const double *mx, const double *my, const double *mz,
+                                             fb200_model **out)
+{
+    if (nprisms < 0 || (nprisms > 0 && (!first_vertex || !vx || !vy || !z1 || !z2)))
+        return fail(FB200_EINVAL, "fb200_model_create_polyprisms: NULL array or negative size");
+    const int nmag = (mx != nullptr) + (my != nullptr) + (mz != nullptr);
+    if (nmag != 0 && nmag != 3) return fail(FB200_EINVAL, "mx, my, mz must be all NULL or all given");
+    // one row per polygon edge: vertex k -> vertex (k+1) % nverts (polyprism.py:264-269)
+    std::vector<double> row[6], dens, mag[3];
+    for (int64_t q = 0; q < nprisms; ++q) {
+        const int64_t v0 = first_vertex[q], nv = first_vertex[q + 1] - v0;
+        if (nv < 1) return fail(FB200_EINVAL, "polygon without vertices");
+        for (int64_t k = 0; k < nv; ++k) {
+            const int64_t a = v0 + k, b = v0 + (k + 1) % nv;
+            row[0].push_back(vx[a]); row[1].push_back(vx[b]);
+            row[2].push_back(vy[a]); row[3].push_back(vy[b]);
+            row[4].push_back(z1[q]); row[5].push_back(z2[q]);
+            if (density) dens.push_back(density[q]);
+            if (nmag == 3) { mag[0].push_back(mx[q]); mag[1].push_back(my[q]); mag[2].push_back(mz[q]); }
+        }
+    }
+    const int64_t m = (int64_t)row[0].size();
+    int rc = fb200_model_create(device, m, row[0].data(), row[1].data(), row[2].data(), row[3].data(),
+                                row[4].data(), row[5].data(), density ? dens.data() : nullptr,
+                                nmag == 3 ? mag[0].data() : nullptr, nmag == 3 ? mag[1].data() : nullptr,
+                                nmag == 3 ? mag[2].data() : nullptr, out);
+    if (rc != FB200_OK) return rc;
+    (*out)->poly_edges = true;
+    return FB200_OK;
+}
+
 extern "C" int fb200_model_attach_mesh(fb200_model *mod, int nx, int ny, int nz, const double *xn,
                                        const double *yn, const double *zn,
                                        const double *cell_size, const double *w_density,
@@ -797,6 +832,7 @@ static int run_set(fb200_model *mod, uint32_t set, uint32_t request, bool exact,
     a.nsplit = (int)nsplit;
     auto launch = [&](const ForwardArgs &args) -> cudaError_t {
         if (mod->spheres) return launch_forward_sphere(set, args, mod->stream);
+        if (mod->poly_edges) return launch_forward_polyprism(set, args, mod->stream);
         if (exact) return launch_forward_exact(set, args, mod->stream);
         return magnetic ? launch_forward_fast_mag(set, args, mod->stream)
                         : launch_forward_fast_grav(set, args, mod->stream);
@@ -840,9 +876,10 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         return fail(FB200_EPROP, "magnetic field requested but the model holds no magnetization");
     if ((mmask & bit(F_TF)) && !fvec)
         return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
-    if (mod->spheres && (field_mask & ~SPHERE_FIELDS))
-        return fail(FB200_EUNSUP, "spheres offer gz, gxx..gzz, tf, bx, by, bz only (sphere.py)");
-    if (mod->spheres && init) return fail(FB200_EUNSUP, "no accumulate entry points for spheres");
+    const bool sibling = mod->spheres || mod->poly_edges;
+    if (sibling && (field_mask & ~SPHERE_FIELDS))
+        return fail(FB200_EUNSUP, "spheres and polygonal prisms offer gz, gxx..gzz, tf, bx, by, bz only");
+    if (sibling && init) return fail(FB200_EUNSUP, "no accumulate entry points for spheres / polygonal prisms");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
     const bool split = !exact && !(flags & FB200_NO_PRISM_SPLIT);
@@ -911,7 +948,7 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
             if (surface) CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
             if (gmask) {
                 const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
-                for (uint32_t set : mod->spheres ? cover(gmask, kSphereGravitySets) : cover(gmask, kGravitySets)) {
+                for (uint32_t set : sibling ? cover(gmask, kSphereGravitySets) : cover(gmask, kGravitySets)) {
                     int rc = surface
                         ? run_set_surface(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, scale, d_out, ld)
                         : use_nodes
@@ -982,6 +1019,8 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
         return fail(FB200_EUNSUP, "unsupported flag for fb200_jacobian");
     if (mod->spheres && !((SPHERE_FIELDS >> field) & 1u))
         return fail(FB200_EUNSUP, "spheres offer gz, gxx..gzz, tf, bx, by, bz only (sphere.py)");
+    if (mod->poly_edges)
+        return fail(FB200_EUNSUP, "fb200_jacobian is not offered for polygonal prisms (rows are edges)");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
     const bool transposed = (flags & FB200_TRANSPOSED) != 0;
@@ -1133,7 +1172,8 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
     if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf requested without the inducing-field direction");
     if (flags & ~(FB200_DEVICE_POINTERS | FB200_REFERENCE_ORDER | FB200_PER_CELL))
         return fail(FB200_EUNSUP, "unsupported flag for fb200_adjoint");
-    if (mod->spheres) return fail(FB200_EUNSUP, "fb200_adjoint is not offered for spheres");
+    if (mod->spheres || mod->poly_edges)
+        return fail(FB200_EUNSUP, "fb200_adjoint is not offered for spheres / polygonal prisms");
     const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
     const bool exact = (flags & FB200_REFERENCE_ORDER) != 0;
     const int64_t m = mod->m;

@@ -21,6 +21,7 @@ cudaError_t launch_adjoint_fast(int field, const AdjointArgs &a, int nsplit, cud
 
 cudaError_t launch_forward_sphere(uint32_t mask, const ForwardArgs &a, cudaStream_t s);                  // fwd_sphere.cu
 cudaError_t launch_jacobian_sphere(int field, bool transposed, const JacobianArgs &a, cudaStream_t s);  // fwd_sphere.cu
+cudaError_t launch_forward_polyprism(uint32_t mask, const ForwardArgs &a, cudaStream_t s);               // fwd_polyprism_exact.cu
 cudaError_t launch_forward_face(uint32_t mask, const ForwardArgs &a, int grid_y, cudaStream_t s);   // fwd_surface.cu
 cudaError_t launch_forward_node(uint32_t mask, const ForwardArgs &a, int grid_y, cudaStream_t s);   // fwd_surface.cu
 cudaError_t launch_forward_node_rev(int field, const ForwardArgs &a, int grid_y, cudaStream_t s);    // fwd_surface.cu

@@ -95,6 +95,31 @@ class Sphere(object):
         return ' | '.join('%s:%g' % (n, v) for n, v in names)
 
 
+class PolygonalPrism(object):
+    """
+    A prism with a polygonal horizontal cross-section.  x -> North, y -> East, z -> Down;
+    ``vertices`` = list of ``[x, y]`` pairs, **clockwise** (the other way round flips the
+    sign, like the reference, geometry.py:502-546); ``z1, z2`` = top and bottom.
+
+    >>> p = PolygonalPrism([[0, 0], [0, 2], [1, 2], [1, 0]], 0, 3, {'density': 50})
+    >>> p.nverts, p.z2
+    (4, 3.0)
+    """
+
+    def __init__(self, vertices, z1, z2, props=None):
+        self.props = props if props is not None else {}
+        self.x = np.array([v[0] for v in vertices], dtype=np.float64)
+        self.y = np.array([v[1] for v in vertices], dtype=np.float64)
+        self.z1, self.z2 = float(z1), float(z2)
+        self.nverts = len(vertices)
+
+    def addprop(self, prop, value):
+        self.props[prop] = value
+
+    def copy(self):
+        return PolygonalPrism(np.transpose([self.x, self.y]), self.z1, self.z2, props=dict(self.props))
+
+
 class _PrismSequence(object):
     """Iteration protocol shared by the two meshes (py2 ``next`` kept too)."""
 

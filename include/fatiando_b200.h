@@ -101,6 +101,19 @@ int fb200_model_create_spheres(int device, int64_t m,
                                const double *radius, const double *density,
                                const double *mx, const double *my, const double *mz,
                                fb200_model **out);
+/* Sibling model family: polygonal prisms (fatiando/gravmag/polyprism.py:19-1076,
+ * Plouff 1976).  Prism q has the polygon vertices
+ * (vx, vy)[first_vertex[q] .. first_vertex[q+1]) (clockwise, like the reference
+ * asks), top z1[q], bottom z2[q] and density and/or magnetization; first_vertex has
+ * nprisms + 1 entries.  The handle works with fb200_forward for the fields
+ * polyprism.py offers (FB200_GZ, FB200_GXX..FB200_GZZ, FB200_TF, FB200_BX/BY/BZ),
+ * with pmag_override for tf (polyprism.py:19); every polygon edge is one staged
+ * row.  Jacobian and adjoint are not offered (FB200_EUNSUP).                    */
+int fb200_model_create_polyprisms(int device, int64_t nprisms, const int64_t *first_vertex,
+                                  const double *vx, const double *vy,
+                                  const double *z1, const double *z2, const double *density,
+                                  const double *mx, const double *my, const double *mz,
+                                  fb200_model **out);
 /* Regular-mesh acceleration (optional).  Declares that the model's prisms are
  * the unmasked cells of a regular nx*ny*nz PrismMesh (mesh.py:495-665) and hands
  * over its node-sharing form: node coordinates xn[nx+1], yn[ny+1], zn[nz+1]

@@ -12,6 +12,8 @@
 #include "../../fatiando_b200/csrc/prism_fast.cuh"
 #include "../../fatiando_b200/csrc/prism_mesh.cuh"
 #include "../../fatiando_b200/csrc/prism_face.cuh"
+#include "../../fatiando_b200/csrc/polyprism.cuh"
+#include "../../fatiando_b200/csrc/sphere.cuh"
 
 using namespace fb200;
 
@@ -125,6 +127,42 @@ extern "C" int hostsim_surface_forward(uint32_t mask, const double *xp, const do
 {
 #define CASE(M) if (mask == (M)) return run_surface<(M)>(xp, yp, zp, n, nf, face, nn, node, cell, out);
     FB200_GRAVITY_SETS(CASE)
+#undef CASE
+    return -1;
+}
+
+// sibling families: rows through an evaluator policy (EvalPolyEdge, EvalSphere)
+template <uint32_t MASK, class Eval>
+static void run_rows(const double *xp, const double *yp, const double *zp, size_t n, size_t m,
+                     const double *const *b, const double *const *p, const double *f, double *out)
+{
+    constexpr int NC = popc(MASK);
+    const double fv[3] = {f[0], f[1], f[2]};
+    for (size_t l = 0; l < n; ++l) {
+        double acc[NC];
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+        for (size_t q = 0; q < m; ++q)
+            Eval::template pair<MASK>(acc, xp[l], yp[l], zp[l], b[0][q], b[1][q], b[2][q], b[3][q],
+                                      b[4][q], b[5][q], p[0][q], p[1] ? p[1][q] : 0.0,
+                                      p[2] ? p[2][q] : 0.0, fv);
+        for (int c = 0; c < NC; ++c) out[(size_t)c * n + l] = acc[c];
+    }
+}
+
+// kind 0: polygon edges, 1: spheres
+extern "C" int hostsim_sibling_forward(int kind, uint32_t mask, const double *xp, const double *yp,
+                                       const double *zp, size_t n, size_t m, const double *const *b,
+                                       const double *const *p, const double *fvec, double *out)
+{
+#define CASE(M)                                                                              \
+    if (mask == (M)) {                                                                       \
+        if (kind == 0) run_rows<(M), EvalPolyEdge>(xp, yp, zp, n, m, b, p, fvec, out);       \
+        else run_rows<(M), EvalSphere>(xp, yp, zp, n, m, b, p, fvec, out);                   \
+        return 0;                                                                            \
+    }
+    CASE(0x008) CASE(0x010) CASE(0x020) CASE(0x040) CASE(0x080) CASE(0x100) CASE(0x200)
+    CASE(0x3F0) CASE(0x3F8)
+    FB200_MAGNETIC_SETS(CASE)
 #undef CASE
     return -1;
 }
