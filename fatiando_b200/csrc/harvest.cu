@@ -137,6 +137,10 @@ struct fb200_harvest {
     int64_t chunk_rows = 0;
     int64_t *d_rows = nullptr;  size_t rows_cap = 0;
     double *d_res = nullptr;    size_t res_cap = 0;
+    // pinned staging of the per-call traffic (candidate rows in, 2 doubles per candidate and
+    // data set out): one async copy each way instead of staged pageable copies
+    int64_t *h_rows = nullptr;
+    double *h_res = nullptr;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     std::mutex lock;
@@ -256,6 +260,8 @@ extern "C" int fb200_harvest_destroy(fb200_harvest *h)
     for (double *p : h->chunks) cudaFree(p);
     cudaFree(h->d_chunks); cudaFree(h->d_xyz); cudaFree(h->d_obs); cudaFree(h->d_w);
     cudaFree(h->d_norm); cudaFree(h->d_off); cudaFree(h->d_pred); cudaFree(h->d_rows); cudaFree(h->d_res);
+    if (h->h_rows) cudaFreeHost(h->h_rows);
+    if (h->h_res) cudaFreeHost(h->h_res);
     if (s) cudaStreamDestroy(s);
     delete h;
     return FB200_OK;
@@ -352,16 +358,21 @@ extern "C" int fb200_harvest_evaluate(fb200_harvest *h, int64_t ncand, const int
     DeviceScope g(h->device);
     if ((size_t)ncand > h->rows_cap) {
         if (h->d_rows) cudaFreeAsync(h->d_rows, h->stream);
+        if (h->h_rows) { cudaStreamSynchronize(h->stream); cudaFreeHost(h->h_rows); h->h_rows = nullptr; }
         h->rows_cap = std::max<size_t>(256, 2 * (size_t)ncand);
         FB_CK(cudaMallocAsync((void **)&h->d_rows, h->rows_cap * sizeof(int64_t), h->stream));
+        FB_CK(cudaMallocHost((void **)&h->h_rows, h->rows_cap * sizeof(int64_t)));
     }
     const size_t nres = 2 * (size_t)ncand * h->ndata;
     if (nres > h->res_cap) {
         if (h->d_res) cudaFreeAsync(h->d_res, h->stream);
+        if (h->h_res) { cudaStreamSynchronize(h->stream); cudaFreeHost(h->h_res); h->h_res = nullptr; }
         h->res_cap = std::max<size_t>(1024, 2 * nres);
         FB_CK(cudaMallocAsync((void **)&h->d_res, h->res_cap * sizeof(double), h->stream));
+        FB_CK(cudaMallocHost((void **)&h->h_res, h->res_cap * sizeof(double)));
     }
-    FB_CK(cudaMemcpyAsync(h->d_rows, rows, (size_t)ncand * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    std::memcpy(h->h_rows, rows, (size_t)ncand * sizeof(int64_t));
+    FB_CK(cudaMemcpyAsync(h->d_rows, h->h_rows, (size_t)ncand * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     EvaluateArgs a;
     a.obs = h->d_obs; a.w = h->d_w; a.pred = h->d_pred; a.off = h->d_off; a.norm = h->d_norm;
     a.chunks = h->d_chunks; a.chunk_rows = h->chunk_rows; a.ntot = h->ntot; a.rows = h->d_rows;
@@ -370,10 +381,11 @@ extern "C" int fb200_harvest_evaluate(fb200_harvest *h, int64_t ncand, const int
     harvest_evaluate_kernel<<<grid, HV_EVAL_THREADS, 0, h->stream>>>(a);
     FB_CK(cudaGetLastError());
     h->launches += 1;
-    const size_t half = (size_t)ncand * h->ndata * sizeof(double);
-    FB_CK(cudaMemcpyAsync(misfit, a.misfit, half, cudaMemcpyDeviceToHost, h->stream));
-    FB_CK(cudaMemcpyAsync(shape, a.shape, half, cudaMemcpyDeviceToHost, h->stream));
+    const size_t half = (size_t)ncand * h->ndata;
+    FB_CK(cudaMemcpyAsync(h->h_res, h->d_res, 2 * half * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     FB_CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(misfit, h->h_res, half * sizeof(double));
+    std::memcpy(shape, h->h_res + half, half * sizeof(double));
     return FB200_OK;
 }
 

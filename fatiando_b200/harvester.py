@@ -438,12 +438,14 @@ def _grow(neighbors, engine, totalmisfit, mu, regularizer, threshold):
     if not neighbors:
         return None, None, None, None
     cands = list(neighbors.values())
-    misfit, shape = engine.evaluate([c._row for c in cands])
+    misfit, shape = engine.evaluate(numpy.fromiter((c._row for c in cands), dtype=numpy.int64,
+                                                   count=len(cands)))
     misfit, shape = _totals(misfit), _totals(shape)
     ok = (misfit < totalmisfit) & (numpy.abs(misfit - totalmisfit) / totalmisfit >= threshold)
     if not ok.any():
         return None, None, None, None
-    reg = regularizer + numpy.array([c.distance for c in cands])
+    reg = regularizer + numpy.fromiter((c.distance for c in cands), dtype=numpy.float64,
+                                       count=len(cands))
     goal = numpy.where(ok, shape + mu * reg, numpy.inf)
     best = int(numpy.argmin(goal))          # first occurrence of the minimum
     return cands[best], float(goal[best]), float(misfit[best]), float(reg[best])
