@@ -89,5 +89,26 @@ def main():
     print('mag: %d accretions' % (len(out['order']) - 1))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--imaging" not in sys.argv:
     main()
+
+
+def imaging_case():
+    """fatiando.gravmag.imaging.migrate on a small synthetic (SURVEY 8(f) row 2's caller)."""
+    hv, prism, geometry, meshmod, utils, grd = reference_modules()
+    sys.modules['fatiando.gravmag'].transform = type(sys)('transform_stub')
+    sys.modules['fatiando.gravmag.transform'] = sys.modules['fatiando.gravmag'].transform
+    sys.modules['fatiando.gravmag'].prism = prism
+    imaging = importlib.import_module('fatiando.gravmag.imaging')
+    model = [geometry.Prism(600, 1400, 700, 1500, 200, 800, {'density': 800})]
+    x, y, z = grd.regular((0, 3000, 0, 3000), (21, 19), z=-20)
+    gz = prism.gz(x, y, z, model)
+    mesh = imaging.migrate(x, y, z, gz, 0, 1200, (6, 9, 10), power=0.7, scale=2.0)
+    np.savez_compressed(os.path.join(HERE, 'imaging_migrate.npz'), x=x, y=y, z=z, gz=gz,
+                        density=np.asarray(mesh.props['density'], dtype=float),
+                        bounds=np.asarray(mesh.bounds, dtype=float), shape=np.array(mesh.shape))
+    print('imaging: density range', float(np.min(mesh.props['density'])), float(np.max(mesh.props['density'])))
+
+
+if __name__ == "__main__" and "--imaging" in sys.argv:
+    imaging_case()
