@@ -405,6 +405,38 @@ def test_node_sharing_jacobian(gpu_lib, oracle):
     assert j.shape == (xa.size, mesh.size) and np.all(j[:, 5] == 0.0)
 
 
+def test_hazard_walls_send_merged_forms_to_the_per_cell_kernels(gpu_lib):
+    """A mesh whose y spacing makes the reference round two shared walls differently
+    (flatten._mismatched_walls): a point lying IN such a wall must be evaluated per cell --
+    forward, Jacobian and adjoint then equal the per-cell kernels bit for bit."""
+    from fatiando_b200 import prism, mesher, gridder
+    from fatiando_b200.flatten import flatten
+    mesh = mesher.PrismMesh((0, 5000, -300, 4100, 10, 2000), (5, 9, 11))
+    mesh.addprop('density', np.random.RandomState(2).uniform(-1000, 1000, mesh.size))
+    flat = flatten(mesh, 'density')
+    hazard_y = flat.nodes.hazard[1]
+    assert hazard_y.size >= 2 and flat.nodes.hazard[0].size == 0
+    xp, yp, zp = gridder.scatter((0, 5000, -300, 4100), 40, z=-80., seed=6)
+    data = np.random.RandomState(3).normal(size=xp.size)
+    with prism.Model(mesh, 'density') as fwd, prism.Model(mesh, None, keep_all=True) as geo:
+        # no point in a hazard wall: the merged forms run (and differ from per cell in the last bits)
+        a = fwd.fields(xp, yp, zp, ['gz', 'gyy'])
+        b = fwd.fields(xp, yp, zp, ['gz', 'gyy'], per_cell=True)
+        assert not np.array_equal(a['gyy'], b['gyy'])
+        ja, jb = geo.jacobian(xp, yp, zp, 'gyy'), geo.jacobian(xp, yp, zp, 'gyy', per_cell=True)
+        assert not np.array_equal(ja, jb)
+        # one point exactly in a mismatched wall: everything falls back
+        yp2 = yp.copy()
+        yp2[7] = hazard_y[0]
+        a = fwd.fields(xp, yp2, zp, ['gz', 'gyy'])
+        b = fwd.fields(xp, yp2, zp, ['gz', 'gyy'], per_cell=True)
+        for f in a:
+            assert np.array_equal(a[f], b[f]), f
+        assert np.array_equal(geo.jacobian(xp, yp2, zp, 'gyy'), geo.jacobian(xp, yp2, zp, 'gyy', per_cell=True))
+        assert np.array_equal(geo.adjoint(xp, yp2, zp, data, 'gz'),
+                              geo.adjoint(xp, yp2, zp, data, 'gz', per_cell=True))
+
+
 def test_relief_surface_form_equals_per_cell_and_oracle(gpu_lib, oracle):
     """PrismRelief on a tight regular grid: surface form (default) against the per-cell kernels
     and the oracle; the thickness-dependent shift case falls back by itself."""
