@@ -490,6 +490,27 @@ def test_relief_surface_form_equals_per_cell_and_oracle(gpu_lib, oracle):
     assert_parity(got, ref, cond, C_FLOOR_FAST, 'override on a relief')
 
 
+def test_relief_at_c5_scale(gpu_lib, oracle):
+    """BASELINE config 5 at full model size (1000x1000 PrismRelief, 1e6 prisms): surface form
+    and per-cell kernels against the oracle on a sample of the 1e6 points, gz + tensor."""
+    import bench
+    from fatiando_b200 import prism
+    from fatiando_b200.flatten import flatten
+    w = bench.make_workload("c5t", 1)
+    idx = np.linspace(0, w['xp'].size - 1, 24).astype(int)
+    xp, yp, zp = (np.ascontiguousarray(w[k][idx]) for k in ('xp', 'yp', 'zp'))
+    flat = flatten(w['model'], 'density')
+    assert flat.size == 1000000 and flat.surface is not None
+    with prism.Model(flat, 'density') as model:
+        surf = model.fields(xp, yp, zp, w['names'])
+        cells = model.fields(xp, yp, zp, w['names'], per_cell=True)
+    for f in w['names']:
+        ref = oracle.model(f, xp, yp, zp, flat.bounds, flat.density[:, None], threads=8)
+        cond = oracle.condition(f, xp, yp, zp, flat.bounds, flat.density[:, None], threads=8)
+        assert_parity(surf[f], ref, cond, C_FLOOR_FAST, 'C5 surface ' + f)
+        assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'C5 per cell ' + f)
+
+
 def test_negative_zero_bounds_and_points_on_planes(gpu_lib, oracle):
     """-0.0 bounds (e.g. z = -1*0.0 from a flat relief) with points in those planes:
     the reference tests `x < 0`, false for -0.0; the kernel reads sign bits, so the
