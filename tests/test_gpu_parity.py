@@ -511,6 +511,45 @@ def test_relief_at_c5_scale(gpu_lib, oracle):
         assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'C5 per cell ' + f)
 
 
+def test_c3_and_c4_at_full_model_size(gpu_lib, oracle):
+    """BASELINE configs 3 and 4 at their full model sizes on samples of their points:
+    tf+bx+by+bz of the 1e5-cell magnetized mesh (node sharing and per cell), and rows of the
+    250000 x 40000 gz sensitivity matrix (node sharing and per cell), against the oracle."""
+    import bench
+    from fatiando_b200 import prism
+    from fatiando_b200.flatten import flatten
+    w = bench.make_workload("c3", 1)
+    idx = np.linspace(0, w['xp'].size - 1, 40).astype(int)
+    xp, yp, zp = (np.ascontiguousarray(w[k][idx]) for k in ('xp', 'yp', 'zp'))
+    flat = flatten(w['model'], 'magnetization', fvec=w['fvec'])
+    with prism.Model(flat, 'magnetization') as model:
+        assert model.nodes is not None
+        nodes = model.fields(xp, yp, zp, w['names'], fvec=w['fvec'])
+        cells = model.fields(xp, yp, zp, w['names'], fvec=w['fvec'], per_cell=True)
+    for f in w['names']:
+        pr = flat.magnetization if f != 'tf' else np.hstack([flat.magnetization,
+                                                             np.tile(w['fvec'], (flat.size, 1))])
+        ref = oracle.model(f, xp, yp, zp, flat.bounds, pr, threads=8)
+        cond = oracle.condition(f, xp, yp, zp, flat.bounds, pr, threads=8)
+        assert_parity(nodes[f], ref, cond, C_FLOOR_FAST, 'C3 nodes ' + f)
+        assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'C3 per cell ' + f)
+    w = bench.make_workload("c4full", 1)
+    idx = np.linspace(0, w['xp'].size - 1, 21).astype(int)
+    xp, yp, zp = (np.ascontiguousarray(w[k][idx]) for k in ('xp', 'yp', 'zp'))
+    flat = flatten(w['model'], None, override=True)
+    with prism.Model(flat, None) as model:
+        assert model.nodes is not None and model.size == 40000
+        jn = model.jacobian(xp, yp, zp, 'gz')
+        jc = model.jacobian(xp, yp, zp, 'gz', per_cell=True)
+    ref = oracle.jacobian('gz', xp, yp, zp, flat.bounds, [1.0], threads=8)
+    for q in range(0, flat.size, 997):
+        bq = [b[q:q + 1] for b in flat.bounds]
+        cond = oracle.condition('gz', xp, yp, zp, bq, np.ones((1, 1)))
+        assert_parity(jn[:, q], ref[:, q], cond, C_FLOOR_FAST, 'C4 node jacobian col %d' % q)
+        assert_parity(jc[:, q], ref[:, q], cond, C_FLOOR_FAST, 'C4 cell jacobian col %d' % q)
+    assert np.max(np.abs(jn - ref)) <= 1e-9 * np.abs(ref).max()
+
+
 def test_negative_zero_bounds_and_points_on_planes(gpu_lib, oracle):
     """-0.0 bounds (e.g. z = -1*0.0 from a flat relief) with points in those planes:
     the reference tests `x < 0`, false for -0.0; the kernel reads sign bits, so the
