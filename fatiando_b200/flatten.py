@@ -90,10 +90,10 @@ def _mesh_bounds(mesh):
     y1 = float(b[2]) + dy * j
     z1 = float(b[4]) + dz * k
     x2, y2, z2 = x1 + dx, y1 + dy, z1 + dz
-    shape = (nz, ny, nx)
-    full = lambda a, axis: np.broadcast_to(
-        a.reshape([-1 if ax == axis else 1 for ax in range(3)]), shape).ravel()
-    return [full(x1, 2), full(x2, 2), full(y1, 1), full(y2, 1), full(z1, 0), full(z2, 0)]
+    along_x = lambda a: np.tile(a, ny * nz)
+    along_y = lambda a: np.tile(np.repeat(a, nx), nz)
+    along_z = lambda a: np.repeat(a, nx * ny)
+    return [along_x(x1), along_x(x2), along_y(y1), along_y(y2), along_z(z1), along_z(z2)]
 
 
 def _relief_bounds(relief):
@@ -113,12 +113,12 @@ def _property_arrays(props, size):
         dens = np.asarray(props['density'])
         if dens.dtype == object or dens.shape != (size,):
             return None, None, True
-        dens = dens.astype(np.float64)
+        dens = np.asarray(dens, dtype=np.float64)
     if 'magnetization' in props:
         mag = np.asarray(props['magnetization'])
         if mag.dtype == object or mag.shape not in ((size,), (size, 3)):
             return None, None, True
-        mag = mag.astype(np.float64)
+        mag = np.asarray(mag, dtype=np.float64)
     return dens, mag, False
 
 
@@ -168,12 +168,10 @@ def _node_weights(values, shape):
     nz, ny, nx = shape
     pad = np.zeros((nz + 2, ny + 2, nx + 2))
     pad[1:-1, 1:-1, 1:-1] = values.reshape(nz, ny, nx)
-    w = np.zeros((nz + 1, ny + 1, nx + 1))
-    for dc in (0, 1):
-        for db in (0, 1):
-            for da in (0, 1):
-                sign = -1.0 if (da + db + dc) % 2 else 1.0
-                w += sign * pad[dc:dc + nz + 1, db:db + ny + 1, da:da + nx + 1]
+    # sum over (dc, db, da) in {0,1}^3 of (-1)^(da+db+dc) pad[c+dc, b+db, a+da]: along every
+    # axis that is (lower neighbour) - (upper neighbour), i.e. minus a forward difference
+    w = np.diff(np.diff(np.diff(pad, axis=2), axis=1), axis=0)
+    np.negative(w, out=w)
     return np.ascontiguousarray(np.transpose(w, (1, 2, 0))).ravel()     # [b][a][c]
 
 
@@ -214,16 +212,17 @@ def mesh_nodes(mesh, prop, fvec=None):
     dx, dy, dz = (float(d) for d in mesh.dims)
     if not (dx > 0 and dy > 0 and dz > 0):
         return None
-    keep = np.ones(size)
-    mask = getattr(mesh, 'mask', None)
-    if mask is not None and len(mask):
-        keep[np.asarray(mask, dtype=np.int64)] = 0.0
     if prop == 'density':
-        channels = [dens * keep]
+        channels = [dens]
     else:
         if mag.ndim == 1:
             mag = _expand_scalar_magnetization(mag, fvec)
-        channels = [mag[:, c] * keep for c in range(3)]
+        channels = [mag[:, c] for c in range(3)]
+    mask = getattr(mesh, 'mask', None)
+    if mask is not None and len(mask):
+        keep = np.ones(size)
+        keep[np.asarray(mask, dtype=np.int64)] = 0.0
+        channels = [ch * keep for ch in channels]
     if not all(np.all(np.isfinite(ch)) for ch in channels):
         return None
     b = mesh.bounds
@@ -255,7 +254,39 @@ class ReliefSurface(object):
         self.hazard = hazard if hazard is not None else [np.zeros(0)] * 3
 
 
-def relief_surface(relief, prop='density'):
+def _grid_axes(x, y):
+    """
+    If the points (x, y) are the nodes of a rectangular grid, each exactly once, return
+    ``(xs, ix, ys, iy)``: the sorted axis coordinates and every point's indices; else None.
+    The raveled-meshgrid orders ``gridder.regular`` produces (x slowest, or y slowest) are
+    recognised in O(n); anything else goes through a sort.
+    """
+    n = x.size
+    for slow, fast in ((x, y), (y, x)):
+        change = np.flatnonzero(slow[1:] != slow[:-1])
+        nfast = int(change[0]) + 1 if change.size else n
+        if n % nfast:
+            continue
+        nslow = n // nfast
+        s2, f2 = slow.reshape(nslow, nfast), fast.reshape(nslow, nfast)
+        sa, fa = s2[:, 0], f2[0]
+        if not (np.all(np.diff(sa) > 0) and np.all(np.diff(fa) > 0)):
+            continue
+        if np.array_equal(s2, np.broadcast_to(sa[:, None], s2.shape)) and \
+                np.array_equal(f2, np.broadcast_to(fa[None, :], f2.shape)):
+            islow = np.repeat(np.arange(nslow), nfast)
+            ifast = np.tile(np.arange(nfast), nslow)
+            return (sa, islow, fa, ifast) if slow is x else (fa, ifast, sa, islow)
+    xs, ix = np.unique(x, return_inverse=True)
+    ys, iy = np.unique(y, return_inverse=True)
+    if xs.size * ys.size != n:
+        return None
+    if np.any(np.bincount(iy * xs.size + ix, minlength=n) != 1):
+        return None
+    return xs, ix, ys, iy
+
+
+def relief_surface(relief, prop='density', bounds=None):
     """
     :class:`ReliefSurface` of ``relief``, or ``None`` when it does not apply: not a
     ``PrismRelief`` with a per-cell density, the nodes are not a regular grid, or the
@@ -274,12 +305,13 @@ def relief_surface(relief, prop='density'):
     if not (dx > 0 and dy > 0 and np.all(np.isfinite(x)) and np.all(np.isfinite(y))
             and np.all(np.isfinite(z))):
         return None
-    xs, ix = np.unique(x, return_inverse=True)
-    ys, iy = np.unique(y, return_inverse=True)
-    nx, ny = xs.size, ys.size
-    if nx * ny != n or np.unique(iy * nx + ix).size != n:
+    grid = _grid_axes(x, y)
+    if grid is None:
         return None
-    bounds = _relief_bounds(relief)
+    xs, ix, ys, iy = grid
+    nx, ny = xs.size, ys.size
+    if bounds is None:
+        bounds = _relief_bounds(relief)
     # neighbouring cells must share their edge up to rounding: xs[a] + dx/2 == xs[a+1] - dx/2
     tol = 8 * np.finfo(float).eps
     for c, h, big in ((xs, 0.5 * dx, np.abs(xs).max()), (ys, 0.5 * dy, np.abs(ys).max())):
@@ -344,7 +376,7 @@ def flatten(prisms, prop=None, override=False, fvec=None):
     nodes = surface = None
     if prop is not None and not override and index.size:
         nodes = mesh_nodes(prisms, prop, fvec=fvec)
-        surface = relief_surface(prisms, prop)
+        surface = relief_surface(prisms, prop, bounds=bounds if index.size == total else None)
     elif index.size == total:
         nodes = mesh_geometry(prisms)          # Jacobian / override models: geometry only
     return FlatModel(bounds, dens, mag, index, total, nodes, surface)
