@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJac
         // (lanes past the end of the slab keep computing -- the warp votes inside node_eval
         // need them -- on the padded tail of zs, and do not store)
         int e = e0, c = c0, ia = a0;
-#pragma unroll 1
+#pragma unroll 2
         for (int it = 0; it < rounds; ++it) {
             const double X = fm::sub(xs[ia], px), Z = fm::sub(zs[c], pz);
             const bool tx = below_2m480(X);
