@@ -285,3 +285,30 @@ def test_relief_surface_form_matches_the_per_cell_reference(hostsim, oracle):
     relief = mesher.PrismRelief(0, (100., 100.), (xs, ys, -np.ones(50)))
     relief.addprop('density', 2670. * np.ones(50))
     assert relief_surface(relief) is None
+
+
+def test_accuracy_against_a_50_digit_evaluation(hostsim, oracle):
+    """the new evaluators are no less accurate than the reference.  Truth = mpmath
+    evaluation of the same sums (tools/accuracy_report.py); every evaluator, and the reference
+    itself, stays within a quarter of eps*A of it on a mesh seen from near and from afar."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import accuracy_report as ar
+    from fatiando_b200 import mesher, gridder
+    from fatiando_b200.flatten import flatten
+    rs = np.random.RandomState(3)
+    mesh = mesher.PrismMesh((0, 5000, -300, 4100, 10, 2000), (2, 3, 3))
+    mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+    flat = flatten(mesh, 'density')
+    for xp, yp, zp in (gridder.scatter((0, 5000, -300, 4100), 5, z=-150., seed=1),
+                       gridder.scatter((-3e5, 3e5, -3e5, 3e5), 5, z=-4e4, seed=2)):
+        for f in ('gz', 'gxx', 'gxy'):
+            t = ar.truth(f, xp, yp, zp, flat.bounds, flat.density)
+            cond = oracle.condition(f, xp, yp, zp, flat.bounds, flat.density[:, None], scale=1.0)
+            got = {'reference': oracle.model(f, xp, yp, zp, flat.bounds, flat.density[:, None], scale=1.0),
+                   'per cell': forward(hostsim, 1 << NAMES.index(f), 0, xp, yp, zp, flat.bounds,
+                                       flat.density[:, None])[0],
+                   'nodes': mesh_forward(hostsim, 1 << NAMES.index(f), xp, yp, zp, flat.nodes)[0]}
+            for name, vals in got.items():
+                err = np.array([abs(ar.mp.mpf(float(v)) - tv) for v, tv in zip(vals, t)], dtype=float)
+                assert np.max(err / (EPS * cond)) < 0.25, (f, name)
