@@ -923,7 +923,8 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
         CK(cudaEventRecord(mod->ev0, mod->stream));
         // a regular mesh with node weights attached: node-sharing kernel, unless the
         // caller overrides the property, wants the reference order or the per-cell path
-        bool nodes_ok = mod->has_mesh && !exact && !init && !(flags & FB200_PER_CELL);
+        bool nodes_ok = mod->has_mesh && !exact && !init && !(flags & FB200_PER_CELL) &&
+                        mod->nzp <= MESH_ZMAX;
         // a relief with its surface form attached: same conditions, gravity only
         bool surface = mod->has_surface && gmask && !exact && !init && !(flags & FB200_PER_CELL) &&
                        !dens_override;

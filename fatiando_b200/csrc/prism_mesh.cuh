@@ -291,7 +291,6 @@ mesh_forward_kernel(const MeshArgs a)
     const int64_t g0 = (int64_t)blockIdx.y * a.chunk;
     const int64_t g1 = (g0 + a.chunk < mv.nnodes) ? g0 + a.chunk : mv.nnodes;
     const int ntiles = (int)((g1 - g0 + TILE - 1) / TILE);
-    const bool z_in_smem = mv.nzp <= MESH_ZMAX;
 
     auto issue = [&](int t, int s) {
         const int64_t off = g0 + (int64_t)t * TILE;
@@ -309,8 +308,9 @@ mesh_forward_kernel(const MeshArgs a)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (z_in_smem)
-        for (int i = threadIdx.x; i < mv.nzp; i += FWD_THREADS) zn_s[i] = mv.zn[i];
+    // the z levels live in shared memory (the host takes the per-cell kernels for meshes
+    // with more than MESH_ZMAX of them)
+    for (int i = threadIdx.x; i < mv.nzp; i += FWD_THREADS) zn_s[i] = mv.zn[i];
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int s = 0; s < FWD_STAGES && s < ntiles; ++s) issue(s, s);
@@ -338,7 +338,7 @@ mesh_forward_kernel(const MeshArgs a)
             // zero weight (uniform region, masked cells): nothing to add -- uniform branch
             const bool live = MAG ? (w0 != 0.0 || w1 != 0.0 || w2 != 0.0) : (w0 != 0.0);
             if (live) {
-                const double Z = fm::sub(z_in_smem ? zn_s[c_] : mv.zn[c_], zp);
+                const double Z = fm::sub(zn_s[c_], zp);
                 node_eval<MASK>(acc, X, Y, Z, sxy, tiny_xy, tiny_x_or_y, w0, w1, w2, f, sh);
             }
             if (++c_ == mv.nzp) {      // next node column: new X (and Y at the end of a row)
@@ -383,7 +383,7 @@ template <uint32_t MASK>
 inline cudaError_t launch_mesh_t(const MeshArgs &a, cudaStream_t stream)
 {
     dim3 grid((unsigned)((a.n + FWD_THREADS - 1) / FWD_THREADS), (unsigned)a.nsplit);
-    const size_t zbytes = a.mesh.nzp <= MESH_ZMAX ? (size_t)a.mesh.nzp * sizeof(double) : 0;
+    const size_t zbytes = (size_t)a.mesh.nzp * sizeof(double);
     mesh_forward_kernel<MASK><<<grid, FWD_THREADS, zbytes, stream>>>(a);
     return cudaGetLastError();
 }
