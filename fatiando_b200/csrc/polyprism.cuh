@@ -11,15 +11,44 @@
 // The arithmetic is the reference's, expression by expression, INCLUDING its
 // `dummy = 1e-10` guards, which differ from kernel to kernel (added to deltax/deltay, p
 // and d for xx, xy, xz, yy, yz; to dist only for zz; inside the logs for gz): parity with
-// the reference near degenerate geometry depends on them.  log / atan2 / sqrt are the
-// library's.  The translation unit is compiled with -fmad=false so that every product
+// the reference near degenerate geometry depends on them.  sqrt and the divisions are IEEE;
+// log / atan2 of ordinary arguments go through the fast-path primitives (pp_log, pp_atan2
+// below), anything else through the library.  The translation unit is compiled with -fmad=false so that every product
 // and sum rounds separately, like numpy.  All requested components share the edge's
 // radii, distances and arctangent differences.
 #pragma once
 #include <cmath>
 #include "prism_common.cuh"
+#include "prism_fastmath.cuh"
 
 namespace fb200 {
+
+// log and atan2 of ordinary arguments by the fast-path primitives (prism_fastmath.cuh: one
+// division + polynomial each, ~1 ulp), the library's for everything else (zeros, denormals,
+// infinities, NaN, negative log arguments) so that the reference's behaviour in degenerate
+// geometry -- which its `dummy` guards are there for -- is untouched.
+FB_HD bool pp_ordinary(double v)          // finite, normal, non-zero
+{
+    const unsigned e = (unsigned)fm::hi32(v) & 0x7ff00000u;
+    return e - 0x00100000u < 0x7fe00000u;
+}
+
+FB_HD double pp_log(double x)
+{
+    if (x > 0.0 && pp_ordinary(x)) return fm::log_ratio(x, 1.0);
+    return log(x);
+}
+
+FB_HD double pp_atan2(double y, double x)
+{
+    if (pp_ordinary(y) && pp_ordinary(x)) {
+        const double r = fm::atan_ratio(y, x);                 // atan(y/x) in [-pi/2, pi/2]
+        if (x > 0.0) return r;
+        const double s = (y < 0.0) ? -1.0 : 1.0;               // x < 0: +-pi on top
+        return fma(s, fm::konst(4), fma(s, fm::konst(5), r));
+    }
+    return atan2(y, x);
+}
 
 struct EvalPolyEdge {
     static constexpr bool NEEDS_FLAG = false;
@@ -60,14 +89,14 @@ struct EvalPolyEdge {
             const double A1 = sqrt(A1s), A2 = sqrt(A2s);
             const double B1 = sqrt(Q1 * Q1 + p_sqr), B2 = sqrt(Q2 * Q2 + p_sqr);
             const double E11 = R11 * B1, E12 = R12 * B2, E21 = R21 * B1, E22 = R22 * B2;
-            double k = (Z2 - Z1) * (atan2(Q2, p) - atan2(Q1, p));
-            k = k + Z2 * (atan2(Z2 * Q1, R21 * p) - atan2(Z2 * Q2, R22 * p));
-            k = k + Z1 * (atan2(Z1 * Q2, R12 * p) - atan2(Z1 * Q1, R11 * p));
+            double k = (Z2 - Z1) * (pp_atan2(Q2, p) - pp_atan2(Q1, p));
+            k = k + Z2 * (pp_atan2(Z2 * Q1, R21 * p) - pp_atan2(Z2 * Q2, R22 * p));
+            k = k + Z1 * (pp_atan2(Z1 * Q2, R12 * p) - pp_atan2(Z1 * Q1, R11 * p));
             const double C1 = Q1 * A1, C2 = Q2 * A2;
             k = k + 0.5 * p * A1 / (B1 + d) *
-                        log((E11 - C1) * (E21 + C1) / ((E11 + C1) * (E21 - C1) + d) + d);
+                        pp_log((E11 - C1) * (E21 + C1) / ((E11 + C1) * (E21 - C1) + d) + d);
             k = k + 0.5 * p * (A2 / (B2 + d)) *
-                        log((E22 - C2) * (E12 + C2) / ((E22 + C2) * (E12 - C2) + d) + d);
+                        pp_log((E22 - C2) * (E12 + C2) / ((E22 + C2) * (E12 - C2) + d) + d);
             acc[c] = acc[c] + k * p0;
             ++c;
         }
@@ -81,8 +110,8 @@ struct EvalPolyEdge {
                 const double dist = sqrt(dx * dx + dy * dy) + d;
                 const double p = (X1 * Y2 - X2 * Y1) / dist;
                 const double d1 = (dx * X1 + dy * Y1) / dist, d2 = (dx * X2 + dy * Y2) / dist;
-                ezz = atan2(Z2 * d2, p * R22) - atan2(Z1 * d2, p * R21) - atan2(Z2 * d1, p * R12) +
-                      atan2(Z1 * d1, p * R11);
+                ezz = pp_atan2(Z2 * d2, p * R22) - pp_atan2(Z1 * d2, p * R21) - pp_atan2(Z2 * d1, p * R12) +
+                      pp_atan2(Z1 * d1, p * R11);
             }
             if constexpr (need_a || need_l) {
                 const double dx = X2 - X1 + d, dy = Y2 - Y1 + d;
@@ -90,10 +119,10 @@ struct EvalPolyEdge {
                 const double d1 = (dx * X1 + dy * Y1) / dist + d, d2 = (dx * X2 + dy * Y2) / dist + d;
                 const double n = dx / dy, m = dy / dx;
                 if constexpr (need_l) {
-                    const double log_r22 = log((R22 - d2) / (R22 + d2) + d);
-                    const double log_r21 = log((R21 - d2) / (R21 + d2) + d);
-                    const double log_r12 = log((R12 - d1) / (R12 + d1) + d);
-                    const double log_r11 = log((R11 - d1) / (R11 + d1) + d);
+                    const double log_r22 = pp_log((R22 - d2) / (R22 + d2) + d);
+                    const double log_r21 = pp_log((R21 - d2) / (R21 + d2) + d);
+                    const double log_r12 = pp_log((R12 - d1) / (R12 + d1) + d);
+                    const double log_r11 = pp_log((R11 - d1) / (R11 + d1) + d);
                     if constexpr (need_xz) {                        // polyprism.py:791-824
                         const double n_sqr_p1 = n * n + 1;
                         const double g = X1 - Y1 * n, ng = n * g;
@@ -113,27 +142,27 @@ struct EvalPolyEdge {
                 }
                 if constexpr (need_a) {
                     const double p = (X1 * Y2 - X2 * Y1) / dist + d;
-                    const double ad2 = atan2(Z2 * d2, p * R22) - atan2(Z1 * d2, p * R21);
-                    const double ad1 = atan2(Z2 * d1, p * R12) - atan2(Z1 * d1, p * R11);
+                    const double ad2 = pp_atan2(Z2 * d2, p * R22) - pp_atan2(Z1 * d2, p * R21);
+                    const double ad1 = pp_atan2(Z2 * d1, p * R12) - pp_atan2(Z1 * d1, p * R11);
                     if constexpr (need_xx) {                        // polyprism.py:617-647
                         const double g = X1 - Y1 * n;
                         double t = g * Y2 * ad2 / (p * d2) + n * p * ad2 / (d2);
                         t = t - (g * Y1 * ad1 / (p * d1) + n * p * ad1 / (d1));
-                        t = t + n * log((Z2 + R12) * (Z1 + R21) / ((Z1 + R11) * (Z2 + R22) + d) + d);
+                        t = t + n * pp_log((Z2 + R12) * (Z1 + R21) / ((Z1 + R11) * (Z2 + R22) + d) + d);
                         exx = t * (-1 / (1 + n * n));
                     }
                     if constexpr (need_xy) {                        // polyprism.py:703-734
                         const double g = X1 - Y1 * n, g_sqr = g * g;
                         double t = (g_sqr + g * n * Y2) * ad2 / (p * d2) - p * ad2 / d2;
                         t = t - ((g_sqr + g * n * Y1) * ad1 / (p * d1) - p * ad1 / d1);
-                        t = t + log((Z2 + R22) * (Z1 + R11) / ((Z1 + R21) * (Z2 + R12) + d) + d);
+                        t = t + pp_log((Z2 + R22) * (Z1 + R11) / ((Z1 + R21) * (Z2 + R12) + d) + d);
                         exy = t * (1 / (1 + n * n));
                     }
                     if constexpr (need_yy) {                        // polyprism.py:880-910
                         const double cc = Y1 - X1 * m;
                         double t = cc * X2 * ad2 / (p * d2) + m * p * ad2 / d2;
                         t = t - (cc * X1 * ad1 / (p * d1) + m * p * ad1 / d1);
-                        t = t + m * log((Z2 + R12) * (Z1 + R21) / ((Z2 + R22) * (Z1 + R11)) + d);
+                        t = t + m * pp_log((Z2 + R12) * (Z1 + R21) / ((Z2 + R22) * (Z1 + R11)) + d);
                         eyy = t * (1 / (1 + m * m));
                     }
                 }
