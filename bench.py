@@ -438,6 +438,12 @@ def run_gpu(args):
                                    "sustained %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 figure"
                                    % (burst.value, sustained.value),
                     "algorithmic_flop_per_pair": wk['flop'], "algorithmic_of": wk['what'],
+                    "note": "achieved = pairs/s x F with F = SURVEY 8(d)'s FLOP per pair of the reference "
+                            "formulation (libm-grade log/atan2 per corner); the kernels reach the same "
+                            "answer with collapsed sums / node sharing in ~190-520 FP64 instructions per "
+                            "pair, so frac exceeds 1; executed_frac = executed FP64-pipe instructions "
+                            "(ncu, profiles/) x pairs/s / (148 SM x 64 lanes x clock) is the measured "
+                            "FP64-pipe utilisation",
                     "executed_fp64_inst_per_pair": executed,
                     "executed_frac": (per_gpu * executed / (148 * 64 * sm_hz)
                                       if executed else None)}
