@@ -239,6 +239,16 @@ def _cpu_chunk(args):
     return out
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(w, flat, seconds=15.0, cores=None):
     """pairs/s of the reference CPU path on a bounded sample of workload w."""
     import multiprocessing as mp
@@ -267,11 +277,19 @@ def cpu_baseline(w, flat, seconds=15.0, cores=None):
         t0 = time.perf_counter()
         pool.map(_cpu_chunk, jobs)
         dt = time.perf_counter() - t0
+        # (i) of BASELINE.md section 3: one core, on one worker's share of the sample
+        t1 = time.perf_counter()
+        pool.map(_cpu_chunk, jobs[:1])
+        dt1 = time.perf_counter() - t1
     pairs = float(n_s) * m
+    one_core = float(jobs[0][1].size) * m / dt1
     return {"value": pairs / dt, "unit": UNIT, "cores": len(jobs),
             "kind": "reference" if po.ref_available() else "port",
-            "sample": "%d of %d points x all %d prisms, %d field call(s) each (%s), %.1f s" % (
-                n_s, w['xp'].size, m, len(w['names']), '+'.join(w['names']), dt),
+            "cpu_model": _cpu_model(), "one_core_value": one_core,
+            "sample": "%d of %d points x all %d prisms, %d field call(s) each (%s), %.1f s on %d cores; "
+                      "one core: %d points, %.1f s" % (
+                          n_s, w['xp'].size, m, len(w['names']), '+'.join(w['names']), dt, len(jobs),
+                          jobs[0][1].size, dt1),
             "seconds": dt}
 
 
@@ -302,7 +320,9 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (seeded)", "config": {"workload": w['label']},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": steps[0]['cores'],
-                             "kind": steps[0]['kind'], "sample": steps[0]['sample']},
+                             "kind": steps[0]['kind'], "sample": steps[0]['sample'],
+                             "cpu_model": steps[0]['cpu_model'],
+                             "one_core_value": float(np.mean([s['one_core_value'] for s in steps]))},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
