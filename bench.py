@@ -70,9 +70,9 @@ EXECUTED_FP64_PER_PAIR = {"c2": 427.7, "c2a": 427.7, "c3": 441.8, "c4": 318.5, "
 # the same for the node-sharing kernel of regular meshes, per CELL x point pair
 # (profiles/r01_c2_tensor_nodes.txt, r01_c3_mag4_nodes.txt)
 EXECUTED_FP64_PER_PAIR_NODES = {"c2": 190.6, "c2a": 190.6, "c3": 209.2,
-                                "c4": 112.9, "c4full": 112.9}      # c4: profiles/r01_c4_jacobian_nodes.txt
+                                "c4": 111.8, "c4full": 111.8}      # c4: profiles/r01_c4_jacobian_nodes.txt
 # and for the surface form of a relief (profiles/r01_c5_gz_surface.txt, r01_c5t_gz_tensor_surface.txt)
-EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 208.6, "c5t": 353.7, "c5full": 208.6, "c5tfull": 353.7}
+EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 207.6, "c5t": 350.7, "c5full": 207.6, "c5tfull": 350.7}
 
 
 # --------------------------------------------------------------------------
