@@ -87,6 +87,23 @@ def main():
                compactness=0.1, threshold=0.001, restrict=json.dumps(['above']))
     np.savez_compressed(os.path.join(HERE, 'harvester_mag.npz'), **out)
     print('mag: %d accretions' % (len(out['order']) - 1))
+    # ---- case C: joint gz + total field, one seed carrying both properties, one only density ----
+    inc, dec = 60.0, -8.0
+    model = [Prism(900, 1700, 800, 1800, 200, 700, {'density': 600, 'magnetization': utils.ang2vec(4, inc, dec)}),
+             Prism(2000, 2600, 1900, 2500, 250, 650, {'density': -400})]
+    x, y, z = grd.regular(bounds[:4], (15, 14), z=-60)
+    gz = prism.gz(x, y, z, model) + rs.normal(0, 0.01, x.size)
+    tf = prism.tf(x, y, z, model, inc, dec) + rs.normal(0, 0.5, x.size)
+    mesh = PrismMesh(bounds, (5, 10, 10))
+    locs = [[1300, 1300, 450, {'density': 600, 'magnetization': 4.0}],
+            [2300, 2200, 450, {'density': -400}]]
+    data = [hv.Gz(x, y, z, gz), hv.TotalField(x, y, z, tf, inc, dec, weights=0.7)]
+    out = run_case(hv, mesh, data, locs, compactness=0.3, threshold=0.0008)
+    out.update(x=x, y=y, z=z, gz=gz, tf=tf, inc=inc, dec=dec, mesh_bounds=np.array(bounds, float),
+               mesh_shape=np.array([5, 10, 10]), locations=json.dumps(locs), compactness=0.3,
+               threshold=0.0008)
+    np.savez_compressed(os.path.join(HERE, 'harvester_joint.npz'), **out)
+    print('joint: %d accretions' % (len(out['order']) - 1))
 
 
 if __name__ == "__main__" and "--imaging" not in sys.argv:
