@@ -132,6 +132,66 @@ def fields_prism_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, fvec=N
     return {nm: total[i] * _prism_api.unit_scale(nm) for i, nm in enumerate(order)}
 
 
+def _gpu_jacobian(device):
+    def evaluate(flat, xp, yp, zp, field, pmag=None, fvec=None, **kw):
+        with _prism_api.Model(flat, None, device=device) as model:
+            return model.jacobian(xp, yp, zp, field, pmag=pmag, fvec=fvec, **kw)
+    return evaluate
+
+
+def _gpu_adjoint(device):
+    def evaluate(flat, xp, yp, zp, data, field, pmag=None, fvec=None, **kw):
+        with _prism_api.Model(flat, None, device=device) as model:
+            return model.adjoint(xp, yp, zp, data, field, pmag=pmag, fvec=fvec, **kw)
+    return evaluate
+
+
+def jacobian_row_sharded(xp, yp, zp, prisms, field='gz', pmag=None, fvec=None, device=None,
+                         evaluate=None, **kw):
+    """
+    The rows of the sensitivity matrix that belong to this rank's slice of the
+    observation points: ``(J[sl, :], sl)``.  Row sharding is the multi-GPU layout of
+    ``J`` (C4: 80 GB = 10 GB per GPU at 8); nothing is exchanged -- consumers work on
+    their row block (``J_r @ p`` is the local slice of the predicted data, ``J_r.T @ d_r``
+    needs one all-reduce, see :func:`adjoint_point_sharded`).
+    """
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    flat = prisms if isinstance(prisms, FlatModel) else flatten(prisms, None, override=True)
+    sl = local_slice(xp.size, rank, world)
+    if evaluate is None:
+        evaluate = _gpu_jacobian(rank if device is None else device)
+    rows = evaluate(flat, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
+                    np.ascontiguousarray(zp[sl]), field, pmag=pmag, fvec=fvec, **kw)
+    return rows, sl
+
+
+def adjoint_point_sharded(xp, yp, zp, prisms, data, field='gz', pmag=None, fvec=None, device=None,
+                          evaluate=None, **kw):
+    """
+    ``J.T @ data`` with the observation points split over the ranks: every rank forms the
+    adjoint of its own points on the fly (J is never stored) and ONE all-reduce adds the
+    per-cell partial sums (NCCL when the tensors live on the GPUs).  This is the exchange
+    step of a row-sharded ``J``; the sum order differs from a single-GPU run, so results
+    agree to rounding.
+    """
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    flat = prisms if isinstance(prisms, FlatModel) else flatten(prisms, None, override=True)
+    sl = local_slice(xp.size, rank, world)
+    if evaluate is None:
+        evaluate = _gpu_adjoint(rank if device is None else device)
+    mine = evaluate(flat, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
+                    np.ascontiguousarray(zp[sl]), np.ascontiguousarray(data[sl]), field,
+                    pmag=pmag, fvec=fvec, **kw)
+    total = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64))
+    if dist.get_backend() == 'nccl':
+        total = total.to(torch.device('cuda', torch.cuda.current_device()))
+    dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    return total.cpu().numpy()
+
+
 def fields_multi_device(xp, yp, zp, prisms, names, devices, dens=None, pmag=None, fvec=None,
                         **kw):
     """

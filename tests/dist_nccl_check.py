@@ -39,6 +39,15 @@ def main():
         ok &= bool(np.array_equal(obs[nm], full[nm]))
         scale = np.abs(full[nm]).max()
         ok &= bool(np.allclose(pri[nm], full[nm], rtol=1e-10, atol=1e-12 * scale))
+    # row-sharded Jacobian (no exchange) and the adjoint's one all-reduce
+    data = np.random.RandomState(4).normal(size=xp.size)
+    with prism.Model(mesh, None, keep_all=True, device=local) as model:
+        jac = model.jacobian(xp, yp, zp, 'gz')
+        adj = model.adjoint(xp, yp, zp, data, 'gz')
+    rows, sl = partition.jacobian_row_sharded(xp, yp, zp, mesh, 'gz', device=local)
+    ok &= bool(np.array_equal(rows, jac[sl]))
+    got = partition.adjoint_point_sharded(xp, yp, zp, mesh, data, 'gz', device=local)
+    ok &= bool(np.allclose(got, adj, rtol=1e-10, atol=1e-12 * np.abs(adj).max()))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

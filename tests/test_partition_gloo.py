@@ -58,8 +58,18 @@ def _worker(rank, world, port, q):
         mine, sl = partition.fields_observation_sharded(xp, yp, zp, mesh, names, gather=False,
                                                         evaluate=_oracle_evaluate)
         pri = partition.fields_prism_sharded(xp, yp, zp, mesh, names, evaluate=_oracle_evaluate)
+        def jac_eval(flat, x, y, z, field, pmag=None, fvec=None, **kw):
+            from oracle import prism_oracle as po
+            return po.jacobian(field, x, y, z, flat.bounds, [1.0])
+
+        def adj_eval(flat, x, y, z, d, field, pmag=None, fvec=None, **kw):
+            return jac_eval(flat, x, y, z, field).T @ d
+        data = np.random.RandomState(5).normal(size=xp.size)
+        rows, slj = partition.jacobian_row_sharded(xp, yp, zp, mesh, 'gz', evaluate=jac_eval)
+        adj = partition.adjoint_point_sharded(xp, yp, zp, mesh, data, 'gz', evaluate=adj_eval)
         q.put((rank, {k: v.copy() for k, v in obs.items()}, (sl.start, sl.stop),
-               {k: v.copy() for k, v in mine.items()}, {k: v.copy() for k, v in pri.items()}))
+               {k: v.copy() for k, v in mine.items()}, {k: v.copy() for k, v in pri.items()},
+               rows.copy(), (slj.start, slj.stop), adj.copy()))
     finally:
         dist.destroy_process_group()
 
@@ -88,7 +98,14 @@ def test_sharding_world_size_2_gloo(oracle):
     full = {nm: oracle.model(nm, xp, yp, zp, flat.bounds, flat.density[:, None])
             for nm in ['gz', 'gzz']}
     covered = np.zeros(xp.size, dtype=int)
-    for rank, obs, (a, b), mine, pri in results:
+    flat_all = flatten(mesh, None, override=True)
+    jac = oracle.jacobian('gz', xp, yp, zp, flat_all.bounds, [1.0])
+    data = np.random.RandomState(5).normal(size=xp.size)
+    for rank, obs, (a, b), mine, pri, rows, (ja, jb), adj in results:
+        # row-sharded Jacobian: each rank holds exactly its rows; the adjoint's all-reduce
+        # gives every rank the full J^T d
+        assert np.array_equal(rows, jac[ja:jb]) and (ja, jb) == (a, b)
+        np.testing.assert_allclose(adj, jac.T @ data, rtol=1e-12, atol=1e-15 * np.abs(jac).max())
         covered[a:b] += 1
         for nm in full:
             # observation sharding: bit-identical to the unsharded run, on every rank
