@@ -176,3 +176,11 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.lower().replace("not the oracle", ""), fn
+
+
+def test_doctests_of_the_host_modules():
+    import doctest
+    from fatiando_b200 import utils, mesher
+    for mod in (utils, mesher):
+        res = doctest.testmod(mod)
+        assert res.failed == 0 and res.attempted > 0, mod.__name__
