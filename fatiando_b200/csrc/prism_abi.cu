@@ -1048,7 +1048,9 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     // for, the node slabs do not fit in shared memory, or a point lies in a hazard wall.
     bool by_nodes = mod->has_mesh && !exact && !(flags & FB200_PER_CELL) &&
                     m == (int64_t)(mod->nxp - 1) * (mod->nyp - 1) * (mod->nzp - 1);
-    int mj_points = 8;
+    // points per block: 4 (two warps per point) measured best at C4 -- 55 KB of slabs per block,
+    // three resident blocks per SM overlap their node and cell phases; fewer when the slabs are large
+    int mj_points = 4;
     if (by_nodes) {
         while (mj_points > 1 && mesh_jacobian_smem(mod->nxp, mod->nzp, mj_points) > (size_t)200 * 1024)
             mj_points /= 2;

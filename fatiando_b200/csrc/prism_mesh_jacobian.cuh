@@ -5,7 +5,7 @@
 // per-corner kernel over the cell's eight corners (_prism.pyx:88-104).  In a regular
 // mesh every interior node is a corner of eight cells, so the per-cell kernels
 // (prism_jacobian.cuh) evaluate it eight times per point.  Here a block takes P
-// points and walks the mesh one node ROW (fixed y) at a time: it evaluates the kernel
+// points (4 by default) and walks the mesh one node ROW (fixed y) at a time: it evaluates the kernel
 // once per (point, node) into shared memory -- one warp-strided slab of
 // (nz+1) x (nx+1) values per point, current and previous row -- and then forms the
 // nx x nz cells between the two rows as signed sums of eight shared-memory values,
@@ -38,7 +38,7 @@ struct MeshJacArgs {
     double *out;
     int64_t ld;
     int transposed;
-    int points;                     // P: points per block, a divisor of 8
+    int points;                     // P: points per block, a divisor of 8 (8 / P warps per point)
 };
 
 #if defined(__CUDACC__)
