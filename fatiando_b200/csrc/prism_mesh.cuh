@@ -12,8 +12,8 @@
 // of the corner the node is in that cell.  W is a 2x2x2 difference stencil of
 // the property field, built once on the host (fatiando_b200/flatten.py).  One
 // kernel evaluation per NODE instead of eight per CELL: per cell-equivalent the
-// six tensor components cost ~175 FP64 instructions instead of ~430, and nodes
-// whose weight is zero (uniform regions, masked cells) are skipped outright.
+// six tensor components cost 191 FP64 instructions instead of 428 (ncu, profiles/),
+// and nodes whose weight is zero (uniform regions, masked cells) are skipped outright.
 //
 // The arithmetic per node is the reference's own: r = sqrt((dx*dx + dy*dy) +
 // dz*dz) with the same association and IEEE sqrt, safe_log / safe_atan2
@@ -22,12 +22,16 @@
 // the per-cell path is (i) a shared node uses ONE coordinate where the
 // reference has x1 + dx of one cell and b0 + dx*(i+1) of the next (equal or one
 // ulp apart) and (ii) the order of the additions -- both far inside the parity
-// floor (tests: tests/test_hostsim.py, tests/test_gpu_parity.py).  The one place
-// where a one-ulp coordinate change matters is where the field itself is
-// discontinuous: observation points INSIDE the body exactly on the line through
-// mesh nodes (cell junctions).  There any two roundings disagree, the reference's
-// own cells with each other included; outside the body the direction-dependent
-// parts cancel along every node column (the weights of a column sum to zero).
+// floor (tests: tests/test_hostsim.py, tests/test_gpu_parity.py).  A one-ulp
+// coordinate change matters in one situation only: a point lying exactly IN a
+// wall whose two roundings differ.  There the reference's two cells see a zero
+// and a +-1-ulp atan2 denominator, their direction-dependent terms need not
+// cancel, and its answer depends on that rounding (by multiples of pi * rho).
+// The flattener lists such walls and calls with a point in one of them are
+// evaluated by the per-cell kernels (fb200_model_set_hazard_planes).  Points
+// inside the body on a line through mesh nodes sit on a genuine discontinuity
+// of the field; there any two roundings disagree, the reference's own cells
+// with each other included.
 #pragma once
 #include "prism_common.cuh"
 #include "prism_fastmath.cuh"
