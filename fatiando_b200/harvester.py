@@ -379,6 +379,17 @@ def _distance(n, m, mesh):
     return sqrt((ni - mi) ** 2 + (nj - mj) ** 2 + (nk - mk) ** 2)
 
 
+def _masked_cells(mesh):
+    """The mesh's masked cells as a set (``mesh[i] is None`` without building a Prism);
+    cached on the mesh and refreshed when its mask list changes."""
+    mask = mesh.mask
+    cache = getattr(mesh, '_fb200_masked', None)
+    if cache is None or cache[0] is not mask or cache[1] != len(mask):
+        cache = (mask, len(mask), frozenset(mask))
+        mesh._fb200_masked = cache
+    return cache[2]
+
+
 def _neighbor_indexes(n, mesh, restrict):
     """
     The up-to-six face neighbours of cell ``n`` that exist and are not masked,
@@ -396,8 +407,25 @@ def _neighbor_indexes(n, mesh, restrict):
         ('east', n + nx, inlayer < nx * (ny - 1)),
         ('west', n - nx, inlayer >= nx),
     )
+    masked = _masked_cells(mesh)
     return [idx for name, idx, ok in candidates
-            if name not in restrict and ok and mesh[idx] is not None]
+            if name not in restrict and ok and idx not in masked]
+
+
+class _CellBounds(object):
+    """The six bounds of an unmasked mesh cell, by the expressions of ``PrismMesh.__getitem__``
+    (mesh.py:629-634) without the ``Prism`` object and its props."""
+    __slots__ = ('x1', 'x2', 'y1', 'y2', 'z1', 'z2')
+
+    def __init__(self, mesh, index):
+        nz, ny, nx = mesh.shape
+        k, rest = divmod(index, nx * ny)
+        j, i = divmod(rest, nx)
+        dx, dy, dz = mesh.dims
+        self.x1 = mesh.bounds[0] + dx * i
+        self.y1 = mesh.bounds[2] + dy * j
+        self.z1 = mesh.bounds[4] + dz * k
+        self.x2, self.y2, self.z2 = self.x1 + dx, self.y1 + dy, self.z1 + dz
 
 
 def _shares_prop(props, other):
@@ -417,7 +445,7 @@ def _get_neighbors(cell, neighborhood, estimate, mesh, engine, restrict):
     indexes = [n for n in _neighbor_indexes(cell.i, mesh, restrict)
                if not _is_neighbor(n, cell.props, neighborhood)
                and not _in_estimate(n, cell.props, estimate)]
-    rows = engine.effects([mesh[i] for i in indexes], cell.props)
+    rows = engine.effects([_CellBounds(mesh, i) for i in indexes], cell.props)
     return dict((i, Neighbor(i, cell.props, cell.seed, _distance(i, cell.seed, mesh), engine, int(r)))
                 for i, r in zip(indexes, rows))
 
