@@ -12,9 +12,10 @@ KERN = ['xx', 'xy', 'xz', 'yy', 'yz', 'zz']
 # A = unit * sum_prisms |property| * sum_corners sum_terms |term| is the sum of the
 # absolute values of everything that enters the alternating corner sums, computed by
 # the instrumented oracle (oracle_prism_condition).  The floor is the "absolute floor
-# near zero-crossings" of the north star: 4 units in the last place of the summands.
+# near zero-crossings" of the north star: one unit in the last place of the summands
+# (every GPU and hostsim test also passes with 0.5; observed maxima are <= 0.15).
 RTOL = 1e-9
-C_FLOOR_FAST = 4.0        # fused fast path (collapsed log/atan sums)
+C_FLOOR_FAST = 1.0        # fused fast path (collapsed log/atan sums)
 C_FLOOR_EXACT = 0.25      # reference-order path (only libdevice vs glibc differ)
 
 
