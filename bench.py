@@ -427,6 +427,12 @@ def run_gpu(args):
         barrier()
         e2e_s = (time.perf_counter() - t1) / e2e_steps
     h2d = (6 + (3 if w['prop'] == 'magnetization' else (1 if w['prop'] else 0))) * m * 8 + 3 * rows_done * 8
+    # the merged forms are uploaded with the model every e2e step as well
+    if model.nodes is not None:
+        h2d += sum(a.nbytes for a in model.nodes.weights) + (model.nodes.xn.nbytes + model.nodes.yn.nbytes
+                                                             + model.nodes.zn.nbytes)
+    if model.surface is not None:
+        h2d += sum(a.nbytes for a in model.surface.faces) + sum(a.nbytes for a in model.surface.nodes)
 
     # ---- reduce over ranks: max time, summed work ----
     stats = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device=tdev)
