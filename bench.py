@@ -65,14 +65,14 @@ WORK = {
 # dram__bytes_write.sum, profiles/r01_*): the model and the points are read once, the
 # outputs (<= 2 MB) stay in L2 until the D2H copy.  Bytes per launch at the profiled size.
 DRAM_TRAFFIC_PER_LAUNCH = {"c2": 1.47e6, "c2a": 1.47e6, "c3": None, "c4": None, "c5": None, "c5t": None}
-EXECUTED_FP64_PER_PAIR = {"c2": 427.7, "c2a": 427.7, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3,
+EXECUTED_FP64_PER_PAIR = {"c2": 421.7, "c2a": 421.7, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3,
                           "c5full": 318.5, "c5tfull": 523.3, "c4full": 318.5}   # profiles/r01_*
 # the same for the node-sharing kernel of regular meshes, per CELL x point pair
 # (profiles/r01_c2_tensor_nodes.txt, r01_c3_mag4_nodes.txt)
-EXECUTED_FP64_PER_PAIR_NODES = {"c2": 190.6, "c2a": 190.6, "c3": 209.2,
-                                "c4": 111.8, "c4full": 111.8}      # c4: profiles/r01_c4_jacobian_nodes.txt
+EXECUTED_FP64_PER_PAIR_NODES = {"c2": 187.3, "c2a": 187.3, "c3": 205.8,
+                                "c4": 109.5, "c4full": 109.5}      # c4: profiles/r01_c4_jacobian_nodes.txt
 # and for the surface form of a relief (profiles/r01_c5_gz_surface.txt, r01_c5t_gz_tensor_surface.txt)
-EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 207.6, "c5t": 350.7, "c5full": 207.6, "c5tfull": 350.7}
+EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 202.5, "c5t": 342.6, "c5full": 202.5, "c5tfull": 342.6}
 
 
 # --------------------------------------------------------------------------
