@@ -184,6 +184,11 @@ class ClockSampler(object):
                  "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            # nvidia-smi needs a moment before its first line: wait for it, so that even a
+            # timed region of a few tens of milliseconds is sampled
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 2.0:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
