@@ -80,6 +80,7 @@ EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 202.5, "c5t": 342.6, "c5full": 202.5, "c
 # --------------------------------------------------------------------------
 def make_workload(name, world=1):
     from fatiando_b200 import mesher, gridder, utils
+    from tools.synthetic import hill
     rs = np.random.RandomState
     if name == "c2":
         mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (20, 50, 50))
@@ -148,9 +149,8 @@ def make_workload(name, world=1):
         r = rs(2)
         h = np.zeros(x.size)
         for _ in range(8):
-            h += r.uniform(500, 4000) * utils.gaussian2d(x, y, r.uniform(5e4, 2e5), r.uniform(5e4, 2e5),
-                                                        r.uniform(0, 1e6), r.uniform(0, 1e6),
-                                                        angle=r.uniform(0, 180))
+            h += r.uniform(500, 4000) * hill(x, y, r.uniform(5e4, 2e5), r.uniform(5e4, 2e5),
+                                             (r.uniform(0, 1e6), r.uniform(0, 1e6)), r.uniform(0, 180))
         h += r.uniform(0, 200, x.size)
         relief = mesher.PrismRelief(0, gridder.spacing(area, shape), (x, y, -h))
         relief.props['density'] = np.where(-h > 0, -2670.0, 2670.0)   # addprop's sign rule, vectorised

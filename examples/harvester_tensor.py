@@ -11,14 +11,15 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fatiando_b200 import gridder, harvester, mesher, prism, utils   # noqa: E402
+from fatiando_b200 import gridder, harvester, mesher, prism   # noqa: E402
+from tools.synthetic import noisy   # noqa: E402
 
 bounds = [0, 5000, 0, 5000, 0, 1500]
 model = [mesher.Prism(500, 4500, 3000, 3500, 200, 700, {'density': 1200}),
          mesher.Prism(3000, 4500, 1800, 2300, 200, 700, {'density': 1200})]
 x, y, z = gridder.regular(bounds[:4], (51, 51), z=-150)
 clean = prism.fields(x, y, z, model, ['gyy', 'gyz', 'gzz'])
-gyy, gyz, gzz = (utils.contaminate(clean[f], 2, seed=k) for k, f in enumerate(['gyy', 'gyz', 'gzz']))
+gyy, gyz, gzz = (noisy(clean[f], 2, seed=k) for k, f in enumerate(['gyy', 'gyz', 'gzz']))
 
 mesh = mesher.PrismMesh(bounds, (15, 50, 50))
 data = [harvester.Gyy(x, y, z, gyy), harvester.Gyz(x, y, z, gyz), harvester.Gzz(x, y, z, gzz)]

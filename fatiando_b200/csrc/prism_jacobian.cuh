@@ -164,9 +164,17 @@ inline cudaError_t launch_jacobian_t(const JacobianArgs &a, bool transposed, cud
                   (unsigned)((a.n + JAC_TILE - 1) / JAC_TILE));
         jacobian_kernel<MASK, Eval><<<grid, JAC_THREADS, 0, stream>>>(a);
     } else {
-        dim3 grid((unsigned)((a.n + JAC_THREADS - 1) / JAC_THREADS),
-                  (unsigned)((a.model.m + JAC_TILE - 1) / JAC_TILE));
-        jacobian_t_kernel<MASK, Eval><<<grid, JAC_THREADS, 0, stream>>>(a);
+        // grid.y is limited to 65535 blocks: walk the prisms in slabs of that many tiles
+        const int64_t slab = (int64_t)65535 * JAC_TILE;
+        for (int64_t q0 = 0; q0 < a.model.m; q0 += slab) {
+            JacobianArgs s = a;
+            s.model.m = (a.model.m - q0 < slab) ? a.model.m - q0 : slab;
+            for (int r = 0; r < 6; ++r) s.model.b[r] = a.model.b[r] + q0;
+            s.out = a.out + q0 * a.ld;
+            dim3 grid((unsigned)((a.n + JAC_THREADS - 1) / JAC_THREADS),
+                      (unsigned)((s.model.m + JAC_TILE - 1) / JAC_TILE));
+            jacobian_t_kernel<MASK, Eval><<<grid, JAC_THREADS, 0, stream>>>(s);
+        }
     }
     return cudaGetLastError();
 }

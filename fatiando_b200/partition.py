@@ -50,6 +50,19 @@ def local_slice(n, rank, world):
     return slice(b[rank], b[rank + 1])
 
 
+def default_device(rank=0):
+    """
+    The CUDA device of this process: LOCAL_RANK under torchrun (the global rank is not a
+    device index on a multi-node job), else the rank modulo the visible devices.
+    """
+    import os
+    if 'LOCAL_RANK' in os.environ:
+        return int(os.environ['LOCAL_RANK'])
+    from . import _lib
+    count = _lib.device_count()
+    return rank % count if count else 0
+
+
 def _dist():
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized():
@@ -92,7 +105,7 @@ def fields_observation_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, 
     flat, prop = _flatten_for(prisms, names, dens, pmag, fvec)
     sl = local_slice(xp.size, rank, world)
     if evaluate is None:
-        evaluate = _gpu_evaluate(rank if device is None else device)
+        evaluate = _gpu_evaluate(default_device(rank) if device is None else device)
     mine = evaluate(flat, prop, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
                     np.ascontiguousarray(zp[sl]), names, dens=dens, pmag=pmag, fvec=fvec, **kw)
     if not gather:
@@ -118,7 +131,7 @@ def fields_prism_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, fvec=N
                      None if flat.magnetization is None else flat.magnetization[sl],
                      flat.index[sl], flat.total)
     if evaluate is None:
-        evaluate = _gpu_evaluate(rank if device is None else device)
+        evaluate = _gpu_evaluate(default_device(rank) if device is None else device)
     mine = evaluate(part, prop, xp, yp, zp, names, dens=dens, pmag=pmag, fvec=fvec,
                     scaled=False, **kw)
     order = sorted(mine)
@@ -160,7 +173,7 @@ def jacobian_row_sharded(xp, yp, zp, prisms, field='gz', pmag=None, fvec=None, d
     flat = prisms if isinstance(prisms, FlatModel) else flatten(prisms, None, override=True)
     sl = local_slice(xp.size, rank, world)
     if evaluate is None:
-        evaluate = _gpu_jacobian(rank if device is None else device)
+        evaluate = _gpu_jacobian(default_device(rank) if device is None else device)
     rows = evaluate(flat, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
                     np.ascontiguousarray(zp[sl]), field, pmag=pmag, fvec=fvec, **kw)
     return rows, sl
@@ -181,7 +194,7 @@ def adjoint_point_sharded(xp, yp, zp, prisms, data, field='gz', pmag=None, fvec=
     flat = prisms if isinstance(prisms, FlatModel) else flatten(prisms, None, override=True)
     sl = local_slice(xp.size, rank, world)
     if evaluate is None:
-        evaluate = _gpu_adjoint(rank if device is None else device)
+        evaluate = _gpu_adjoint(default_device(rank) if device is None else device)
     mine = evaluate(flat, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
                     np.ascontiguousarray(zp[sl]), np.ascontiguousarray(data[sl]), field,
                     pmag=pmag, fvec=fvec, **kw)

@@ -69,11 +69,13 @@ class Model(object):
 
     def fields(self, xp, yp, zp, names, dens=None, pmag=None, fvec=None, scaled=True):
         xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
-        ids = sorted(_lib.FIELD_ID[nm] for nm in names)
+        ids = sorted(set(_lib.FIELD_ID[nm] for nm in names))
         n = xp.size
         out = numpy.zeros((len(ids), n), dtype=numpy.float64)
         if n and self.size:
-            mask = sum(1 << i for i in ids)
+            mask = 0
+            for i in ids:
+                mask |= 1 << i
             scale = numpy.array([unit_scale(_lib.FIELDS[i]) if scaled else 1.0 for i in ids])
             dens_arr = None if dens is None else numpy.array([float(dens)])
             pmag_arr = None if pmag is None else numpy.ascontiguousarray(pmag, dtype=numpy.float64)

@@ -39,59 +39,6 @@ def vec2ang(vector):
     return [intensity, r2d * numpy.arcsin(z / intensity), r2d * numpy.arctan2(y, x)]
 
 
-def gaussian2d(x, y, sigma_x, sigma_y, x0=0, y0=0, angle=0.0):
-    """
-    Non-normalised 2-D Gaussian bump (fatiando/utils.py:530-567); used to build
-    the synthetic topography of the relief benchmark.
-    """
-    theta = -1 * angle * numpy.pi / 180.
-    tmpx = 1. / sigma_x ** 2
-    tmpy = 1. / sigma_y ** 2
-    sintheta = numpy.sin(theta)
-    costheta = numpy.cos(theta)
-    a = tmpx * costheta + tmpy * sintheta ** 2
-    b = (tmpy - tmpx) * costheta * sintheta
-    c = tmpx * sintheta ** 2 + tmpy * costheta ** 2
-    xhat = x - x0
-    yhat = y - y0
-    return numpy.exp(-(a * xhat ** 2 + 2. * b * xhat * yhat + c * yhat ** 2))
-
-
-def contaminate(data, stddev, percent=False, return_stddev=False, seed=None):
-    """
-    Add pseudorandom, zero-mean gaussian noise to ``data`` (an array, or a list of arrays
-    with a list of ``stddev``), like the reference's ``utils.contaminate``
-    (utils.py:420-505): the noise vector has its mean removed; ``percent=True`` takes
-    ``stddev`` as a fraction of ``max(abs(data))``; the same ``seed`` gives the same noise as
-    the reference (numpy's legacy generator).
-
-    >>> import numpy as np
-    >>> noisy = contaminate(np.ones(5), 0.1, seed=0)
-    >>> print(np.array2string(noisy, precision=8))
-    [1.03137726 0.89498775 0.95284582 1.07906135 1.04172782]
-    >>> noisy, std = contaminate(np.ones(5), 0.05, seed=0, percent=True, return_stddev=True)
-    >>> print(std)
-    0.05
-    """
-    rng = numpy.random.RandomState(seed)
-    single = not isinstance(stddev, list)
-    stddevs = [stddev] if single else list(stddev)
-    arrays = [data] if single else list(data)
-    contam = []
-    for i, arr in enumerate(arrays):
-        if stddevs[i] == 0.:
-            contam.append(arr)
-            continue
-        if percent:
-            stddevs[i] = stddevs[i] * max(abs(arr))
-        noise = rng.normal(scale=stddevs[i], size=len(arr))
-        noise -= noise.mean()
-        contam.append(numpy.array(arr) + noise)
-    if single:
-        contam, stddevs = contam[0], stddevs[0]
-    return [contam, stddevs] if return_stddev else contam
-
-
 class SparseList(object):
     """
     A fixed-length list that stores only the entries that were set; everything

@@ -3,8 +3,8 @@ Parity of the CUDA path with the oracle and the golden vectors (needs a GPU).
 
 Everything goes through the C ABI (ctypes -> libfatiando_b200.so).  Tolerance
 (helpers.py): |new - ref| <= 1e-9*|ref| + c*eps*A with A the sum of
-absolute terms from the instrumented oracle; c = 4 for the fused fast path,
-c = 0.25 for the reference-order path.
+absolute terms from the instrumented oracle; c = helpers.C_FLOOR_FAST for the fused
+fast path and the merged forms, c = helpers.C_FLOOR_EXACT for the reference-order path.
 """
 import numpy as np
 import pytest

@@ -25,6 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import test_hostsim as th                      # noqa: E402
 from fatiando_b200 import mesher, gridder, utils   # noqa: E402
+from tools.synthetic import hill   # noqa: E402
 from fatiando_b200.flatten import flatten     # noqa: E402
 from oracle import prism_oracle as oracle     # noqa: E402
 
@@ -107,7 +108,7 @@ def main():
     # ---- a relief miniature (1 km cells), points 5 km above ----
     area, shape = (0, 12e3, 0, 12e3), (12, 12)
     x, y = gridder.regular(area, shape)
-    h = 2500 * utils.gaussian2d(x, y, 3e3, 4e3, 5e3, 7e3) + rs.uniform(0, 200, x.size)
+    h = 2500 * hill(x, y, 3e3, 4e3, (5e3, 7e3)) + rs.uniform(0, 200, x.size)
     relief = mesher.PrismRelief(0, gridder.spacing(area, shape)[::-1], (x, y, -h))
     relief.addprop('density', 2670. * np.ones(x.size))
     flat = flatten(relief, 'density')
