@@ -1,6 +1,7 @@
 // harvest.cuh -- effect rows of the planting inversion's candidates (see harvest.cu).
 #pragma once
 #include "prism_common.cuh"
+#include "prism_fastmath.cuh"
 
 namespace fb200 {
 
@@ -24,6 +25,10 @@ __global__ void __launch_bounds__(HV_THREADS) harvest_effect_kernel(const Effect
 {
     const int64_t l = (int64_t)blockIdx.x * HV_THREADS + threadIdx.x;
     const int c = blockIdx.y;
+    if constexpr (Eval::USES_TABLES) {
+        fm::load_tables();
+        __syncthreads();
+    }
     if (l >= a.n) return;
     double acc[1] = {0.0};
     if (a.has[c]) {

@@ -52,6 +52,7 @@ FB_HD double pp_atan2(double y, double x)
 
 struct EvalPolyEdge {
     static constexpr bool NEEDS_FLAG = false;
+    static constexpr bool USES_TABLES = false;
     template <uint32_t MASK>
     static FB_HD_M void pair(double (&acc)[popc(MASK)], double xp, double yp, double zp,
                            double vx1, double vx2, double vy1, double vy2, double z1, double z2,

@@ -289,6 +289,7 @@ Contribution<popc(MASK)> face_careful(double xp, double yp, double zp, double x1
 #endif
 struct EvalFace {
     static constexpr bool NEEDS_FLAG = false;
+    static constexpr bool USES_TABLES = true;
     template <uint32_t MASK>
     static FB_HD_M void pair(double (&acc)[popc(MASK)], double xp, double yp, double zp,
                            double x1, double x2, double y1, double y2, double zf, double zo,
@@ -313,6 +314,7 @@ struct EvalFace {
 // *flag and the host re-evaluates the call cell by cell.
 struct EvalNode {
     static constexpr bool NEEDS_FLAG = true;
+    static constexpr bool USES_TABLES = true;
     template <uint32_t MASK>
     static FB_HD_M void pair_flag(double (&acc)[popc(MASK)], double xp, double yp, double zp,
                                 double xn, double shx, double yn, double shy, double zn, double,
@@ -324,7 +326,8 @@ struct EvalNode {
             if (Z == 0.0 && ((X == 0.0 && Y < 0.0) || (Y == 0.0 && X < 0.0))) *flag = 1;
         }
         const double sh[3] = {shx, shy, 0.0};
-        node_accumulate<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), w, 0.0, 0.0, f, sh);
+        const bool tx = below_2m480(X), ty = below_2m480(Y);
+        node_eval<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), tx & ty, tx | ty, w, 0.0, 0.0, f, sh);
     }
 };
 
@@ -335,6 +338,7 @@ struct EvalNode {
 // Rows: xpt, shx, ypt, shy, zpt, shz, w0 [, w1, w2]   (sh = 1e-5 * cell size).
 struct EvalNodeRev {
     static constexpr bool NEEDS_FLAG = false;
+    static constexpr bool USES_TABLES = true;
     template <uint32_t MASK>
     static FB_HD_M void pair(double (&acc)[popc(MASK)], double xn, double yn, double zn,
                            double xpt, double shx, double ypt, double shy, double zpt, double shz,

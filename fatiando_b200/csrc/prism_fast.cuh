@@ -467,6 +467,7 @@ FB_HD void pair_fast(double (&acc)[popc(MASK)], double xp, double yp, double zp,
 
 struct EvalFast {
     static constexpr bool NEEDS_FLAG = false;
+    static constexpr bool USES_TABLES = true;    // log / atan tables of prism_fastmath.cuh
     template <uint32_t MASK>
     static FB_HD_M void pair(double (&acc)[popc(MASK)], double xp, double yp, double zp,
                            double x1, double x2, double y1, double y2, double z1, double z2,

@@ -16,6 +16,7 @@
 //     chunk order, so results are reproducible run to run.
 #pragma once
 #include "prism_common.cuh"
+#include "prism_fastmath.cuh"
 
 namespace fb200 {
 
@@ -126,6 +127,7 @@ forward_kernel(const ForwardArgs a)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if constexpr (Eval::USES_TABLES) fm::load_tables();
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int s = 0; s < FWD_STAGES && s < ntiles; ++s) issue(s, s);

@@ -19,6 +19,7 @@
 // reported as a secondary counter.
 #pragma once
 #include "prism_common.cuh"
+#include "prism_fastmath.cuh"
 
 namespace fb200 {
 
@@ -57,6 +58,7 @@ jacobian_kernel(const JacobianArgs a)
         pts[1][idx] = a.yp[l0 + idx];
         pts[2][idx] = a.zp[l0 + idx];
     }
+    if constexpr (Eval::USES_TABLES) fm::load_tables();
     __syncthreads();
     double *row = a.out + l0 * a.ld + q;
 #pragma unroll 1
@@ -86,6 +88,7 @@ jacobian_t_kernel(const JacobianArgs a)
     for (int idx = threadIdx.x; idx < cnt; idx += JAC_THREADS)
 #pragma unroll
         for (int r = 0; r < 6; ++r) sp[r][idx] = a.model.b[r][q0 + idx];
+    if constexpr (Eval::USES_TABLES) fm::load_tables();
     __syncthreads();
     double *col = a.out + q0 * a.ld + l;
 #pragma unroll 1
@@ -127,6 +130,7 @@ adjoint_kernel(const AdjointArgs a)
     const int64_t l_begin = (int64_t)blockIdx.y * a.rows_per_split;
     const int64_t l_end = (l_begin + a.rows_per_split < a.j.n) ? l_begin + a.rows_per_split : a.j.n;
     double acc[1] = {0.0};
+    if constexpr (Eval::USES_TABLES) fm::load_tables();     // the loop opens with a block barrier
     for (int64_t l0 = l_begin; l0 < l_end; l0 += JAC_TILE) {
         const int cnt = (l_end - l0 < JAC_TILE) ? (int)(l_end - l0) : JAC_TILE;
         __syncthreads();

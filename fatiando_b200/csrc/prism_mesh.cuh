@@ -39,99 +39,31 @@
 
 namespace fb200 {
 
-// log(a) for a >= 0 with safe_log(0) = 0 (_prism.pyx:28-34)
+// log(a) for a >= 0 with safe_log(0) = 0 (_prism.pyx:28-34); denormal arguments (outside the
+// table logarithm's range) go to the library.  Only on the careful paths.
 FB_HD double node_log(double a)
 {
-    const double arg = (a == 0.0) ? 1.0 : a;
-    return fm::log_ratio(arg, 1.0);
+    if (fm::hi32(a) < 0x00100000) return (a == 0.0) ? 0.0 : log(a);
+    return fm::log_tab(a);
 }
 
-// safe_atan2(y, x) = atan(y / x) folded to [-pi/2, pi/2], 0 for y == 0 (_prism.pyx:16-26)
-FB_HD double node_atan(double y, double x)
+// |safe_atan2(y, x)| = atan(|y| / |x|), 0 for y == 0 (_prism.pyx:16-26); ay = |y|, ax = |x|
+FB_HD double node_atan_abs(double ay, double ax)
 {
     // (0, 0) -> 0: give the division a non-zero denominator
-    const double xs = (x == 0.0 && y == 0.0) ? 1.0 : x;
-    return fm::atan_ratio(y, xs);
+    const double xs = (ax == 0.0 && ay == 0.0) ? 1.0 : ax;
+    return fm::atan_tab(ay, xs);
 }
 
-// Contribution of one node to every requested component.
-//   X, Y, Z  : node - point;  XX_YY = X*X + Y*Y (hoisted per node column);
-//   w0..w2   : node weight (density stencil, or the three magnetization stencils);
-//   sh[3]    : 1e-5 * cell size in x, y, z (the singularity shift, _prism.pyx:327-330)
-template <uint32_t MASK>
-FB_HD void node_accumulate(double (&acc)[popc(MASK)], double X, double Y, double Z,
-                           double XX_YY, double w0, double w1, double w2,
-                           const double (&f)[3], const double (&sh)[3])
-{
-    using namespace fm;
-    const double ZZ = mul(Z, Z);
-    const double r2 = add(XX_YY, ZZ);
-    double r = root(r2);
-    // a node on (or within 2^-485 of) the point: outside the range of the
-    // branch-free root, take the library's
-    if (hi32(r2) < 0x03500000) r = sqrt(r2);
-    double Lx = 0, Ly = 0, Lz = 0, Axx = 0, Ayy = 0, Azz = 0;
-    if constexpr (MASK & NEED_LX) Lx = node_log(add(X, r));
-    if constexpr (MASK & NEED_LY) Ly = node_log(add(Y, r));
-    if constexpr (MASK & NEED_LZ) Lz = node_log(add(Z, r));
-    if constexpr (MASK & NEED_AXX) Axx = node_atan(mul(Z, Y), mul(X, r));
-    if constexpr (MASK & NEED_AYY) Ayy = node_atan(mul(Z, X), mul(Y, r));
-    if constexpr (MASK & NEED_AZZ) Azz = node_atan(mul(X, Y), mul(Z, r));
-    int c = 0;
-    if constexpr (MASK & bit(F_POT))     // _prism.pyx:36-39
-        acc[c++] += (X * Y * Lz + Y * Z * Lx + X * Z * Ly - 0.5 * (X * X) * Axx
-                     - 0.5 * (Y * Y) * Ayy - 0.5 * ZZ * Azz) * w0;
-    if constexpr (MASK & bit(F_GX)) acc[c++] += (X * Axx - (Y * Lz + Z * Ly)) * w0;   // :43-44
-    if constexpr (MASK & bit(F_GY)) acc[c++] += (Y * Ayy - (Z * Lx + X * Lz)) * w0;   // :46-47
-    if constexpr (MASK & bit(F_GZ)) acc[c++] += (Z * Azz - (X * Ly + Y * Lx)) * w0;   // :49-50
-    if constexpr (MASK & bit(F_GXX)) acc[c++] -= Axx * w0;                            // :52-53
-    if constexpr (MASK & bit(F_GXY)) {                                                // :55-56
-        double L = Lz;
-        if (X == 0.0 && Y == 0.0 && Z < 0.0)
-            L = safe_log_ref(add(Z, sqrt(add(add(mul(sh[0], sh[0]), mul(sh[1], sh[1])), ZZ))));
-        acc[c++] += L * w0;
-    }
-    if constexpr (MASK & bit(F_GXZ)) {                                                // :58-59
-        double L = Ly;
-        if (X == 0.0 && Z == 0.0 && Y < 0.0)
-            L = safe_log_ref(add(Y, sqrt(add(add(mul(sh[0], sh[0]), mul(sh[2], sh[2])), mul(Y, Y)))));
-        acc[c++] += L * w0;
-    }
-    if constexpr (MASK & bit(F_GYY)) acc[c++] -= Ayy * w0;                            // :61-62
-    if constexpr (MASK & bit(F_GYZ)) {                                                // :64-65
-        double L = Lx;
-        if (Y == 0.0 && Z == 0.0 && X < 0.0)
-            L = safe_log_ref(add(X, sqrt(add(add(mul(sh[1], sh[1]), mul(sh[2], sh[2])), mul(X, X)))));
-        acc[c++] += L * w0;
-    }
-    if constexpr (MASK & bit(F_GZZ)) acc[c++] -= Azz * w0;                            // :67-68
-    if constexpr (MASK & MAGNETIC_MASK) {
-        // v1..v6 of _prism.pyx:94-99 at this node; w0..w2 are the stencils of mx, my, mz
-        const double bx = fma(-Axx, w0, fma(Lz, w1, Ly * w2));
-        const double by = fma(Lz, w0, fma(-Ayy, w1, Lx * w2));
-        const double bz = fma(Ly, w0, fma(Lx, w1, -Azz * w2));
-        if constexpr (MASK & bit(F_TF)) acc[c++] += fma(f[0], bx, fma(f[1], by, f[2] * bz));
-        if constexpr (MASK & bit(F_BX)) acc[c++] += bx;
-        if constexpr (MASK & bit(F_BY)) acc[c++] += by;
-        if constexpr (MASK & bit(F_BZ)) acc[c++] += bz;
-    }
-}
-
-
-// ---- hot / careful split ---------------------------------------------------------
-// Every special case of the reference (safe_log(0), safe_atan2(0, 0), the shifted r,
-// a root argument below the range of the branch-free root) needs coordinate
-// differences that are zero (or below 2^-480) on TWO axes at once, or a log argument
-// that rounds to zero.  node_eval tests exactly that with exponent compares on the
-// ALU pipe; if ANY lane of the warp has such a node (warp vote: no divergence) the
-// warp takes the out-of-line node_accumulate above, otherwise the straight-line code
-// below, which carries no compares, selects or branches for them.
-FB_HD bool below_2m480(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
+FB_HD double xor_sign(double a, int sg) { return fm::mk(fm::hi32(a) ^ sg, fm::lo32(a)); }
 
 // the six per-corner primitives of one node, plus the logs gxy / gxz / gyz use (equal to
-// Lz / Ly / Lx unless the reference shifts r, _prism.pyx:327-330, :359-362, :418-421)
+// Lz / Ly / Lx unless the reference shifts r, _prism.pyx:327-330, :359-362, :418-421).
+// The three arctangents of a node, atan(ZY / Xr), atan(ZX / Yr), atan(XY / Zr), all have the
+// sign of X*Y*Z: they are evaluated on absolute values and `sg` (0 or 0x80000000) is that sign.
 struct NodePrims {
     double Lx, Ly, Lz, Axx, Ayy, Azz, Lxy, Lxz, Lyz;
+    int sg;
 };
 
 // with every special case of the reference; out of line, rare
@@ -144,7 +76,7 @@ static
 NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double s0, double s1, double s2)
 {
     using namespace fm;
-    NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const double ZZ = mul(Z, Z);
     const double r2 = add(XX_YY, ZZ);
     double r = root(r2);
@@ -152,9 +84,10 @@ NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double 
     if constexpr (MASK & NEED_LX) p.Lx = node_log(add(X, r));
     if constexpr (MASK & NEED_LY) p.Ly = node_log(add(Y, r));
     if constexpr (MASK & NEED_LZ) p.Lz = node_log(add(Z, r));
-    if constexpr (MASK & NEED_AXX) p.Axx = node_atan(mul(Z, Y), mul(X, r));
-    if constexpr (MASK & NEED_AYY) p.Ayy = node_atan(mul(Z, X), mul(Y, r));
-    if constexpr (MASK & NEED_AZZ) p.Azz = node_atan(mul(X, Y), mul(Z, r));
+    if constexpr (MASK & NEED_AXX) p.Axx = node_atan_abs(mul(fabs(Z), fabs(Y)), mul(fabs(X), r));
+    if constexpr (MASK & NEED_AYY) p.Ayy = node_atan_abs(mul(fabs(Z), fabs(X)), mul(fabs(Y), r));
+    if constexpr (MASK & NEED_AZZ) p.Azz = node_atan_abs(mul(fabs(X), fabs(Y)), mul(fabs(Z), r));
+    p.sg = (hi32(X) ^ hi32(Y) ^ hi32(Z)) & (int)0x80000000;
     p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
     if constexpr (MASK & bit(F_GXY))
         if (X == 0.0 && Y == 0.0 && Z < 0.0)
@@ -168,14 +101,21 @@ NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double 
     return p;
 }
 
+// ---- hot / careful split ---------------------------------------------------------
+// Every special case of the reference (safe_log(0), safe_atan2(0, 0), the shifted r,
+// a root argument below the range of the branch-free root) needs coordinate
+// differences that are zero (or below 2^-480) on TWO axes at once, or a log argument
+// that rounds to zero.  node_prims tests exactly that with exponent compares on the
+// ALU pipe; if ANY lane of the warp has such a node (warp vote: no divergence) the
+// warp takes the out-of-line careful variant above, otherwise the straight-line code
+// below, which carries no compares, selects or branches for them.  Both give the same
+// bits for an ordinary node, so a point's result does not depend on its warp-mates.
+FB_HD bool below_2m480(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
+
 // tiny_xy = X and Y both below 2^-480; tiny_x_or_y = one of them is (both per node column).
-// The sums below are written with explicit fma / separately rounded products so that a
-// node gives the same bits whichever way its primitives were obtained (the choice is
-// per WARP, and a point must not change its result with its warp-mates: shard invariance).
 template <uint32_t MASK>
-FB_HD void node_eval(double (&acc)[popc(MASK)], double X, double Y, double Z, double XX_YY,
-                     bool tiny_xy, bool tiny_x_or_y, double w0, double w1, double w2,
-                     const double (&f)[3], const double (&sh)[3])
+FB_HD NodePrims node_prims(double X, double Y, double Z, double XX_YY, bool tiny_xy, bool tiny_x_or_y,
+                           const double (&sh)[3])
 {
     using namespace fm;
     const double ZZ = mul(Z, Z);
@@ -189,54 +129,94 @@ FB_HD void node_eval(double (&acc)[popc(MASK)], double X, double Y, double Z, do
 #if defined(__CUDA_ARCH__)
     bad = __any_sync(0xffffffffu, bad);
 #endif
-    NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (bad) {
-        p = node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2]);
-    } else {
-        if constexpr (MASK & NEED_LX) p.Lx = log_ratio(ax, 1.0);
-        if constexpr (MASK & NEED_LY) p.Ly = log_ratio(ay, 1.0);
-        if constexpr (MASK & NEED_LZ) p.Lz = log_ratio(az, 1.0);
-        if constexpr (MASK & NEED_AXX) p.Axx = atan_ratio(mul(Z, Y), mul(X, r));
-        if constexpr (MASK & NEED_AYY) p.Ayy = atan_ratio(mul(Z, X), mul(Y, r));
-        if constexpr (MASK & NEED_AZZ) p.Azz = atan_ratio(mul(X, Y), mul(Z, r));
-        p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
+    if (bad) return node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2]);
+    NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if constexpr (MASK & NEED_LX) p.Lx = log_tab(ax);
+    if constexpr (MASK & NEED_LY) p.Ly = log_tab(ay);
+    if constexpr (MASK & NEED_LZ) p.Lz = log_tab(az);
+    if constexpr (MASK & NEED_AXX) p.Axx = atan_tab(mul(fabs(Z), fabs(Y)), mul(fabs(X), r));
+    if constexpr (MASK & NEED_AYY) p.Ayy = atan_tab(mul(fabs(Z), fabs(X)), mul(fabs(Y), r));
+    if constexpr (MASK & NEED_AZZ) p.Azz = atan_tab(mul(fabs(X), fabs(Y)), mul(fabs(Z), r));
+    p.sg = (hi32(X) ^ hi32(Y) ^ hi32(Z)) & (int)0x80000000;
+    p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
+    (void)ax; (void)ay; (void)az;
+    return p;
+}
+
+// Adds one node's contribution to every requested component (kernel table of
+// _prism.pyx:36-68; w0..w2 = node weight: density stencil, or the three magnetization
+// stencils).  Explicit fma / separately rounded products: the same bits on every path.
+template <uint32_t MASK>
+FB_HD void node_add(double (&acc)[popc(MASK)], const NodePrims &p, double X, double Y, double Z,
+                    double w0, double w1, double w2, const double (&f)[3])
+{
+    using namespace fm;
+    constexpr uint32_t MIXED = bit(F_POT) | bit(F_GX) | bit(F_GY) | bit(F_GZ) | MAGNETIC_MASK;
+    // signed arctangents where a field mixes them with other terms; the pure-arctangent
+    // fields gxx / gyy / gzz flip the sign of the weight instead (one XOR for all three)
+    double Axx = p.Axx, Ayy = p.Ayy, Azz = p.Azz;
+    if constexpr (MASK & MIXED) {
+        Axx = xor_sign(p.Axx, p.sg); Ayy = xor_sign(p.Ayy, p.sg); Azz = xor_sign(p.Azz, p.sg);
     }
+    const double ws = xor_sign(w0, p.sg);
     int c = 0;
     if constexpr (MASK & bit(F_POT)) {   // _prism.pyx:36-39
         const double logs = fma(mul(X, Y), p.Lz, fma(mul(Y, Z), p.Lx, mul(mul(X, Z), p.Ly)));
-        const double atans = fma(mul(X, X), p.Axx, fma(mul(Y, Y), p.Ayy, mul(ZZ, p.Azz)));
+        const double atans = fma(mul(X, X), Axx, fma(mul(Y, Y), Ayy, mul(mul(Z, Z), Azz)));
         acc[c] = fma(fma(-0.5, atans, logs), w0, acc[c]);
         ++c;
     }
     if constexpr (MASK & bit(F_GX)) {    // :43-44
-        acc[c] = fma(fma(X, p.Axx, -fma(Y, p.Lz, mul(Z, p.Ly))), w0, acc[c]);
+        acc[c] = fma(fma(X, Axx, -fma(Y, p.Lz, mul(Z, p.Ly))), w0, acc[c]);
         ++c;
     }
     if constexpr (MASK & bit(F_GY)) {    // :46-47
-        acc[c] = fma(fma(Y, p.Ayy, -fma(Z, p.Lx, mul(X, p.Lz))), w0, acc[c]);
+        acc[c] = fma(fma(Y, Ayy, -fma(Z, p.Lx, mul(X, p.Lz))), w0, acc[c]);
         ++c;
     }
     if constexpr (MASK & bit(F_GZ)) {    // :49-50
-        acc[c] = fma(fma(Z, p.Azz, -fma(X, p.Ly, mul(Y, p.Lx))), w0, acc[c]);
+        acc[c] = fma(fma(Z, Azz, -fma(X, p.Ly, mul(Y, p.Lx))), w0, acc[c]);
         ++c;
     }
-    if constexpr (MASK & bit(F_GXX)) { acc[c] = fma(-p.Axx, w0, acc[c]); ++c; }   // :52-53
+    if constexpr (MASK & bit(F_GXX)) { acc[c] = fma(-p.Axx, ws, acc[c]); ++c; }   // :52-53
     if constexpr (MASK & bit(F_GXY)) { acc[c] = fma(p.Lxy, w0, acc[c]); ++c; }    // :55-56
     if constexpr (MASK & bit(F_GXZ)) { acc[c] = fma(p.Lxz, w0, acc[c]); ++c; }    // :58-59
-    if constexpr (MASK & bit(F_GYY)) { acc[c] = fma(-p.Ayy, w0, acc[c]); ++c; }   // :61-62
+    if constexpr (MASK & bit(F_GYY)) { acc[c] = fma(-p.Ayy, ws, acc[c]); ++c; }   // :61-62
     if constexpr (MASK & bit(F_GYZ)) { acc[c] = fma(p.Lyz, w0, acc[c]); ++c; }    // :64-65
-    if constexpr (MASK & bit(F_GZZ)) { acc[c] = fma(-p.Azz, w0, acc[c]); ++c; }   // :67-68
+    if constexpr (MASK & bit(F_GZZ)) { acc[c] = fma(-p.Azz, ws, acc[c]); ++c; }   // :67-68
     if constexpr (MASK & MAGNETIC_MASK) {
         // v1..v6 of _prism.pyx:94-99 at this node (unshifted); w0..w2 = stencils of mx, my, mz
-        const double bx = fma(-p.Axx, w0, fma(p.Lz, w1, mul(p.Ly, w2)));
-        const double by = fma(p.Lz, w0, fma(-p.Ayy, w1, mul(p.Lx, w2)));
-        const double bz = fma(p.Ly, w0, fma(p.Lx, w1, mul(-p.Azz, w2)));
+        const double bx = fma(-Axx, w0, fma(p.Lz, w1, mul(p.Ly, w2)));
+        const double by = fma(p.Lz, w0, fma(-Ayy, w1, mul(p.Lx, w2)));
+        const double bz = fma(p.Ly, w0, fma(p.Lx, w1, mul(-Azz, w2)));
         if constexpr (MASK & bit(F_TF)) { acc[c] = add(acc[c], fma(f[0], bx, fma(f[1], by, mul(f[2], bz)))); ++c; }
         if constexpr (MASK & bit(F_BX)) { acc[c] = add(acc[c], bx); ++c; }
         if constexpr (MASK & bit(F_BY)) { acc[c] = add(acc[c], by); ++c; }
         if constexpr (MASK & bit(F_BZ)) { acc[c] = add(acc[c], bz); ++c; }
     }
-    (void)ax; (void)ay; (void)az;
+    (void)ws; (void)Axx; (void)Ayy; (void)Azz;
+}
+
+// one node, hot path with the careful variant chosen by warp vote
+template <uint32_t MASK>
+FB_HD void node_eval(double (&acc)[popc(MASK)], double X, double Y, double Z, double XX_YY,
+                     bool tiny_xy, bool tiny_x_or_y, double w0, double w1, double w2,
+                     const double (&f)[3], const double (&sh)[3])
+{
+    const NodePrims p = node_prims<MASK>(X, Y, Z, XX_YY, tiny_xy, tiny_x_or_y, sh);
+    node_add<MASK>(acc, p, X, Y, Z, w0, w1, w2, f);
+}
+
+// one node with every special case of the reference applied inline (no warp vote): the
+// careful paths of the relief surface form (prism_face.cuh) and its merged nodes
+//   sh[3] : 1e-5 * cell size in x, y, z (the singularity shift, _prism.pyx:327-330)
+template <uint32_t MASK>
+FB_HD void node_accumulate(double (&acc)[popc(MASK)], double X, double Y, double Z,
+                           double XX_YY, double w0, double w1, double w2,
+                           const double (&f)[3], const double (&sh)[3])
+{
+    const NodePrims p = node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2]);
+    node_add<MASK>(acc, p, X, Y, Z, w0, w1, w2, f);
 }
 
 #if defined(__CUDACC__)
@@ -315,6 +295,7 @@ mesh_forward_kernel(const MeshArgs a)
     // the z levels live in shared memory (the host takes the per-cell kernels for meshes
     // with more than MESH_ZMAX of them)
     for (int i = threadIdx.x; i < mv.nzp; i += FWD_THREADS) zn_s[i] = mv.zn[i];
+    fm::load_tables();
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int s = 0; s < FWD_STAGES && s < ntiles; ++s) issue(s, s);

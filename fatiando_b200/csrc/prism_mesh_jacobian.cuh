@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJac
     double *zs = xs + nxp;                         // node z coordinates
     for (int i = threadIdx.x; i < nxp; i += MJ_THREADS) xs[i] = a.xn[i];
     for (int i = threadIdx.x; i < nzp + MJ_ZPAD; i += MJ_THREADS) zs[i] = a.zn[i < nzp ? i : nzp - 1];
+    fm::load_tables();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = warp % P;                        // this warp's point within the block

@@ -23,6 +23,7 @@ constexpr uint32_t SPHERE_FIELDS = bit(F_GZ) | bit(F_GXX) | bit(F_GXY) | bit(F_G
 
 struct EvalSphere {
     static constexpr bool NEEDS_FLAG = false;
+    static constexpr bool USES_TABLES = false;
     template <uint32_t MASK>
     static FB_HD_M void pair(double (&acc)[popc(MASK)], double xp, double yp, double zp,
                            double xc, double volume, double yc, double, double zc, double,

@@ -179,3 +179,12 @@ extern "C" void hostsim_div(const double *a, const double *b, size_t n, double *
 {
     for (size_t i = 0; i < n; ++i) out[i] = fm::div_fast(a[i], b[i]);
 }
+extern "C" void hostsim_log_tab(const double *a, const double *unused, size_t n, double *out)
+{
+    (void)unused;
+    for (size_t i = 0; i < n; ++i) out[i] = fm::log_tab(a[i]);
+}
+extern "C" void hostsim_atan_tab(const double *im, const double *re, size_t n, double *out)
+{
+    for (size_t i = 0; i < n; ++i) out[i] = fm::atan_ratio_tab(im[i], re[i]);
+}

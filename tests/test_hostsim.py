@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, load_golden
-from helpers import C_FLOOR_FAST, EPS, assert_parity, golden_model
+from helpers import C_FLOOR_FAST, EPS, assert_parity, floor_fast, golden_model
 
 HS_DIR = os.path.join(ROOT, "tests", "hostsim")
 dp = ctypes.POINTER(ctypes.c_double)
@@ -66,7 +66,7 @@ def check_sets(H, oracle, sets, xp, yp, zp, b, props, f=(0, 0, 0), what=''):
             ref, cond = cache[fld]
             # host build of the reference-order evaluator: same libm, same order -> same bits
             assert np.array_equal(exact[c], ref), '%s %s exact' % (what, fld)
-            worst = max(worst, assert_parity(fast[c], ref, cond, C_FLOOR_FAST,
+            worst = max(worst, assert_parity(fast[c], ref, cond, floor_fast(b[0].size),
                                              '%s %s in set 0x%x' % (what, fld, mask)))
     return worst
 
