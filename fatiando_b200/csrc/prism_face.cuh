@@ -326,8 +326,7 @@ struct EvalNode {
             if (Z == 0.0 && ((X == 0.0 && Y < 0.0) || (Y == 0.0 && X < 0.0))) *flag = 1;
         }
         const double sh[3] = {shx, shy, 0.0};
-        const bool tx = below_2m480(X), ty = below_2m480(Y);
-        node_eval<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), tx & ty, tx | ty, w, 0.0, 0.0, f, sh);
+        node_eval<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), column_bits(X, Y), w, 0.0, 0.0, f, sh, fm::tab_ref());
     }
 };
 
@@ -347,8 +346,7 @@ struct EvalNodeRev {
         using namespace fm;
         const double X = add(sub(xn, xpt), 0.0), Y = add(sub(yn, ypt), 0.0), Z = add(sub(zn, zpt), 0.0);
         const double sh[3] = {shx, shy, shz};
-        const bool tx = below_2m480(X), ty = below_2m480(Y);
-        node_eval<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), tx & ty, tx | ty, w0, w1, w2, f, sh);
+        node_eval<MASK>(acc, X, Y, Z, add(mul(X, X), mul(Y, Y)), column_bits(X, Y), w0, w1, w2, f, sh, fm::tab_ref());
     }
 };
 

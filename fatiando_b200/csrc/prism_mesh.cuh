@@ -41,18 +41,18 @@ namespace fb200 {
 
 // log(a) for a >= 0 with safe_log(0) = 0 (_prism.pyx:28-34); denormal arguments (outside the
 // table logarithm's range) go to the library.  Only on the careful paths.
-FB_HD double node_log(double a)
+FB_HD double node_log(double a, fm::tabref_t tb)
 {
     if (fm::hi32(a) < 0x00100000) return (a == 0.0) ? 0.0 : log(a);
-    return fm::log_tab(a);
+    return fm::log_tab(a, tb);
 }
 
 // |safe_atan2(y, x)| = atan(|y| / |x|), 0 for y == 0 (_prism.pyx:16-26); ay = |y|, ax = |x|
-FB_HD double node_atan_abs(double ay, double ax)
+FB_HD double node_atan_abs(double ay, double ax, fm::tabref_t tb)
 {
     // (0, 0) -> 0: give the division a non-zero denominator
     const double xs = (ax == 0.0 && ay == 0.0) ? 1.0 : ax;
-    return fm::atan_tab(ay, xs);
+    return fm::atan_tab(ay, xs, tb);
 }
 
 FB_HD double xor_sign(double a, int sg) { return fm::mk(fm::hi32(a) ^ sg, fm::lo32(a)); }
@@ -73,7 +73,8 @@ __device__ __noinline__
 #else
 static
 #endif
-NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double s0, double s1, double s2)
+NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double s0, double s1, double s2,
+                             fm::tabref_t tb)
 {
     using namespace fm;
     NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -81,12 +82,12 @@ NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double 
     const double r2 = add(XX_YY, ZZ);
     double r = root(r2);
     if (hi32(r2) < 0x03500000) r = sqrt(r2);      // outside the range of the branch-free root
-    if constexpr (MASK & NEED_LX) p.Lx = node_log(add(X, r));
-    if constexpr (MASK & NEED_LY) p.Ly = node_log(add(Y, r));
-    if constexpr (MASK & NEED_LZ) p.Lz = node_log(add(Z, r));
-    if constexpr (MASK & NEED_AXX) p.Axx = node_atan_abs(mul(fabs(Z), fabs(Y)), mul(fabs(X), r));
-    if constexpr (MASK & NEED_AYY) p.Ayy = node_atan_abs(mul(fabs(Z), fabs(X)), mul(fabs(Y), r));
-    if constexpr (MASK & NEED_AZZ) p.Azz = node_atan_abs(mul(fabs(X), fabs(Y)), mul(fabs(Z), r));
+    if constexpr (MASK & NEED_LX) p.Lx = node_log(add(X, r), tb);
+    if constexpr (MASK & NEED_LY) p.Ly = node_log(add(Y, r), tb);
+    if constexpr (MASK & NEED_LZ) p.Lz = node_log(add(Z, r), tb);
+    if constexpr (MASK & NEED_AXX) p.Axx = node_atan_abs(mul(fabs(Z), fabs(Y)), mul(fabs(X), r), tb);
+    if constexpr (MASK & NEED_AYY) p.Ayy = node_atan_abs(mul(fabs(Z), fabs(X)), mul(fabs(Y), r), tb);
+    if constexpr (MASK & NEED_AZZ) p.Azz = node_atan_abs(mul(fabs(X), fabs(Y)), mul(fabs(Z), r), tb);
     p.sg = (hi32(X) ^ hi32(Y) ^ hi32(Z)) & (int)0x80000000;
     p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
     if constexpr (MASK & bit(F_GXY))
@@ -112,31 +113,54 @@ NodePrims node_prims_careful(double X, double Y, double Z, double XX_YY, double 
 // bits for an ordinary node, so a point's result does not depend on its warp-mates.
 FB_HD bool below_2m480(double d) { return (fm::hi32(d) & 0x7ff00000) < 0x21f00000; }
 
-// tiny_xy = X and Y both below 2^-480; tiny_x_or_y = one of them is (both per node column).
+// The coordinate part of the test, "X and Y tiny, or Z and one of them", is carried by two
+// integers per node COLUMN (column_bits): zmask = 0 if X and Y are both below 2^-480, else the
+// exponent mask; zor = 0 if one of them is, else the exponent mask.  Then
+// (hi32(Z) & zmask) | zor is below the exponent of 2^-480 exactly in that case: one LOP3 and
+// one compare per node.
+FB_HD int imin(int a, int b) { return a < b ? a : b; }
+struct ColumnBits { int zmask, zor; };
+FB_HD ColumnBits column_bits(double X, double Y)
+{
+    const bool tx = below_2m480(X), ty = below_2m480(Y);
+    ColumnBits c;
+    c.zmask = (tx & ty) ? 0 : 0x7ff00000;
+    c.zor = (tx | ty) ? 0 : 0x7ff00000;
+    return c;
+}
+
+FB_HD bool bad_coordinates(ColumnBits cb, double Z)
+{
+    return ((fm::hi32(Z) & cb.zmask) | cb.zor) < 0x21f00000;
+}
+
+// bad_coord: X and Y both below 2^-480, or Z and one of them (bad_coordinates, or the caller's own test)
 template <uint32_t MASK>
-FB_HD NodePrims node_prims(double X, double Y, double Z, double XX_YY, bool tiny_xy, bool tiny_x_or_y,
-                           const double (&sh)[3])
+FB_HD NodePrims node_prims(double X, double Y, double Z, double XX_YY, bool bad_coord,
+                           const double (&sh)[3], fm::tabref_t tb)
 {
     using namespace fm;
     const double ZZ = mul(Z, Z);
     const double r = root(add(XX_YY, ZZ));
     double ax = 1.0, ay = 1.0, az = 1.0;
-    bool bad = tiny_xy | (below_2m480(Z) & tiny_x_or_y);
+    bool bad = bad_coord;
     // X + r >= +0: zero (or denormal) iff the high word is below the smallest normal's
-    if constexpr (MASK & NEED_LX) { ax = add(X, r); bad = bad | (hi32(ax) < 0x00100000); }
-    if constexpr (MASK & NEED_LY) { ay = add(Y, r); bad = bad | (hi32(ay) < 0x00100000); }
-    if constexpr (MASK & NEED_LZ) { az = add(Z, r); bad = bad | (hi32(az) < 0x00100000); }
+    int lowest = 0x7fffffff;
+    if constexpr (MASK & NEED_LX) { ax = add(X, r); lowest = imin(lowest, hi32(ax)); }
+    if constexpr (MASK & NEED_LY) { ay = add(Y, r); lowest = imin(lowest, hi32(ay)); }
+    if constexpr (MASK & NEED_LZ) { az = add(Z, r); lowest = imin(lowest, hi32(az)); }
+    bad = bad | (lowest < 0x00100000);
 #if defined(__CUDA_ARCH__)
     bad = __any_sync(0xffffffffu, bad);
 #endif
-    if (bad) return node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2]);
+    if (bad) return node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2], tb);
     NodePrims p = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if constexpr (MASK & NEED_LX) p.Lx = log_tab(ax);
-    if constexpr (MASK & NEED_LY) p.Ly = log_tab(ay);
-    if constexpr (MASK & NEED_LZ) p.Lz = log_tab(az);
-    if constexpr (MASK & NEED_AXX) p.Axx = atan_tab(mul(fabs(Z), fabs(Y)), mul(fabs(X), r));
-    if constexpr (MASK & NEED_AYY) p.Ayy = atan_tab(mul(fabs(Z), fabs(X)), mul(fabs(Y), r));
-    if constexpr (MASK & NEED_AZZ) p.Azz = atan_tab(mul(fabs(X), fabs(Y)), mul(fabs(Z), r));
+    if constexpr (MASK & NEED_LX) p.Lx = log_tab(ax, tb);
+    if constexpr (MASK & NEED_LY) p.Ly = log_tab(ay, tb);
+    if constexpr (MASK & NEED_LZ) p.Lz = log_tab(az, tb);
+    if constexpr (MASK & NEED_AXX) p.Axx = atan_tab(mul(fabs(Z), fabs(Y)), mul(fabs(X), r), tb);
+    if constexpr (MASK & NEED_AYY) p.Ayy = atan_tab(mul(fabs(Z), fabs(X)), mul(fabs(Y), r), tb);
+    if constexpr (MASK & NEED_AZZ) p.Azz = atan_tab(mul(fabs(X), fabs(Y)), mul(fabs(Z), r), tb);
     p.sg = (hi32(X) ^ hi32(Y) ^ hi32(Z)) & (int)0x80000000;
     p.Lxy = p.Lz; p.Lxz = p.Ly; p.Lyz = p.Lx;
     (void)ax; (void)ay; (void)az;
@@ -200,10 +224,10 @@ FB_HD void node_add(double (&acc)[popc(MASK)], const NodePrims &p, double X, dou
 // one node, hot path with the careful variant chosen by warp vote
 template <uint32_t MASK>
 FB_HD void node_eval(double (&acc)[popc(MASK)], double X, double Y, double Z, double XX_YY,
-                     bool tiny_xy, bool tiny_x_or_y, double w0, double w1, double w2,
-                     const double (&f)[3], const double (&sh)[3])
+                     ColumnBits cb, double w0, double w1, double w2,
+                     const double (&f)[3], const double (&sh)[3], fm::tabref_t tb)
 {
-    const NodePrims p = node_prims<MASK>(X, Y, Z, XX_YY, tiny_xy, tiny_x_or_y, sh);
+    const NodePrims p = node_prims<MASK>(X, Y, Z, XX_YY, bad_coordinates(cb, Z), sh, tb);
     node_add<MASK>(acc, p, X, Y, Z, w0, w1, w2, f);
 }
 
@@ -215,7 +239,7 @@ FB_HD void node_accumulate(double (&acc)[popc(MASK)], double X, double Y, double
                            double XX_YY, double w0, double w1, double w2,
                            const double (&f)[3], const double (&sh)[3])
 {
-    const NodePrims p = node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2]);
+    const NodePrims p = node_prims_careful<MASK>(X, Y, Z, XX_YY, sh[0], sh[1], sh[2], fm::tab_ref());
     node_add<MASK>(acc, p, X, Y, Z, w0, w1, w2, f);
 }
 
@@ -297,6 +321,9 @@ mesh_forward_kernel(const MeshArgs a)
     for (int i = threadIdx.x; i < mv.nzp; i += FWD_THREADS) zn_s[i] = mv.zn[i];
     fm::load_tables();
     __syncthreads();
+    // shared-window addresses held in registers (see fm::tab_ref_pinned)
+    const fm::tabref_t tb = fm::tab_ref_pinned();
+    const unsigned zbase = fm::pin_u32(smem_u32(zn_s)), zend = zbase + 8u * (unsigned)mv.nzp;
     if (threadIdx.x == 0) {
         for (int s = 0; s < FWD_STAGES && s < ntiles; ++s) issue(s, s);
     }
@@ -308,7 +335,8 @@ mesh_forward_kernel(const MeshArgs a)
     int a_ = (int)(col - (int64_t)b_ * mv.nxp);
     double X = fm::sub(mv.xn[a_], xp), Y = fm::sub(mv.yn[b_ < mv.nyp ? b_ : mv.nyp - 1], yp);
     double sxy = fm::add(fm::mul(X, X), fm::mul(Y, Y));
-    bool tiny_xy = below_2m480(X) & below_2m480(Y), tiny_x_or_y = below_2m480(X) | below_2m480(Y);
+    ColumnBits cb = column_bits(X, Y);
+    unsigned zaddr = zbase + 8u * (unsigned)c_;
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % FWD_STAGES;
@@ -323,11 +351,12 @@ mesh_forward_kernel(const MeshArgs a)
             // zero weight (uniform region, masked cells): nothing to add -- uniform branch
             const bool live = MAG ? (w0 != 0.0 || w1 != 0.0 || w2 != 0.0) : (w0 != 0.0);
             if (live) {
-                const double Z = fm::sub(zn_s[c_], zp);
-                node_eval<MASK>(acc, X, Y, Z, sxy, tiny_xy, tiny_x_or_y, w0, w1, w2, f, sh);
+                const double Z = fm::sub(fm::lds_f64(zaddr), zp);
+                node_eval<MASK>(acc, X, Y, Z, sxy, cb, w0, w1, w2, f, sh, tb);
             }
-            if (++c_ == mv.nzp) {      // next node column: new X (and Y at the end of a row)
-                c_ = 0;
+            zaddr += 8u;
+            if (zaddr == zend) {      // next node column: new X (and Y at the end of a row)
+                zaddr = zbase;
                 if (++a_ == mv.nxp) {
                     a_ = 0;
                     ++b_;
@@ -335,8 +364,7 @@ mesh_forward_kernel(const MeshArgs a)
                 }
                 X = fm::sub(mv.xn[a_], xp);
                 sxy = fm::add(fm::mul(X, X), fm::mul(Y, Y));
-                tiny_xy = below_2m480(X) & below_2m480(Y);
-                tiny_x_or_y = below_2m480(X) | below_2m480(Y);
+                cb = column_bits(X, Y);
             }
         }
         __syncwarp();

@@ -42,16 +42,18 @@ struct MeshJacArgs {
 };
 
 #if defined(__CUDACC__)
+// 3 resident blocks of 256 threads per SM (85 registers): node and cell phases of different
+// blocks overlap.  All shared-memory traffic of the two loops goes through explicit 32-bit
+// shared-window addresses held in registers (fm::pin_u32), advanced by adds -- the index
+// arithmetic the compiler generates for the (level, x) walk was a third of the instruction stream.
 template <uint32_t MASK, bool TRANSPOSED>
-__global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJacArgs a)
+__global__ void __launch_bounds__(MJ_THREADS, 3) mesh_jacobian_kernel(const MeshJacArgs a)
 {
     static_assert(popc(MASK) == 1, "one field per Jacobian");
     extern __shared__ double sm[];
-    // everything the loops read, once, into registers (not re-fetched from the parameter bank)
     const int P = a.points;
     const int nxp = a.nxp, nzp = a.nzp, nx = nxp - 1, nz = nzp - 1, ny = a.nyp - 1;
     const int slab = nzp * nxp;
-    const double scale = a.scale;
     const int64_t ld = a.ld;
     const double *const yn = a.yn;
     double *buf0 = sm, *buf1 = sm + (size_t)P * slab;
@@ -70,36 +72,50 @@ __global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJac
     const double px = a.xp[l], py = a.yp[l], pz = a.zp[l];
     const double f[3] = {a.fvec[0], a.fvec[1], a.fvec[2]};
     const double sh[3] = {a.sh[0], a.sh[1], a.sh[2]};
-    const double u0 = a.unit_p[0], u1 = a.unit_p[1], u2 = a.unit_p[2];
+    // the unit conversion rides on the unit property: every node value is already scaled
+    const double u0 = a.unit_p[0] * a.scale, u1 = a.unit_p[1] * a.scale, u2 = a.unit_p[2] * a.scale;
     // C-order: entry (l, col) at out[l*ld + col]; transposed: out[col*ld + l]
     double *const row_base = TRANSPOSED ? a.out + l : a.out + l * ld;
     __syncthreads();
+    const fm::tabref_t tb = fm::tab_ref_pinned();
+    const unsigned xs_a = fm::pin_u32(smem_u32(xs)), zs_a = fm::pin_u32(smem_u32(zs));
+    // (byte strides pinned too: derived from kernel parameters they would be re-formed from
+    // uniform registers at every use)
+    const unsigned slab_b = fm::pin_u32(8u * (unsigned)slab), row_b = fm::pin_u32(8u * (unsigned)nxp);
+    const unsigned xs_end = xs_a + row_b;
 
     const int step = 32 * nsub;
     const int rounds = (slab + step - 1) / step;   // same trip count for every lane (warp votes inside)
     const int dq = step / nxp, dr = step - dq * nxp;        // one step in (level, x index) form
-    double *cur = buf0 + (size_t)p * slab, *prev = buf1 + (size_t)p * slab;
+    const unsigned step_b = fm::pin_u32(8u * (unsigned)step), dq_b = fm::pin_u32(8u * (unsigned)dq),
+                   dr_b = fm::pin_u32(8u * (unsigned)dr);
+    unsigned cur = fm::pin_u32(smem_u32(buf0 + (size_t)p * slab)), prev = fm::pin_u32(smem_u32(buf1 + (size_t)p * slab));
     const int e0 = sub * 32 + lane;
     const int c0 = e0 / nxp, a0 = e0 - c0 * nxp;
     for (int b = 0; b <= ny; ++b) {
         const double Y = fm::sub(yn[b], py);
         const double YY = fm::mul(Y, Y);
-        const bool ty = below_2m480(Y);
+        const bool ty = below_2m480(Y);            // warp-uniform: the warp has ONE point
         // ---- one kernel evaluation per (point, node) of this row ----
-        // (lanes past the end of the slab keep computing -- the warp votes inside node_eval
+        // (lanes past the end of the slab keep computing -- the warp votes inside node_prims
         // need them -- on the padded tail of zs, and do not store)
-        int e = e0, c = c0, ia = a0;
+        unsigned ea = cur + 8u * (unsigned)e0, za = zs_a + 8u * (unsigned)c0, xa = xs_a + 8u * (unsigned)a0;
+        const unsigned e_end = cur + slab_b;
 #pragma unroll 2
         for (int it = 0; it < rounds; ++it) {
-            const double X = fm::sub(xs[ia], px), Z = fm::sub(zs[c], pz);
-            const bool tx = below_2m480(X);
+            const double X = fm::sub(fm::lds_f64(xa), px), Z = fm::sub(fm::lds_f64(za), pz);
+            // X and Z both below 2^-480 (with Y there too, rare and warp-uniform, the whole row
+            // takes the careful variant: same bits, only slower)
+            const int ex = fm::hi32(X) & 0x7ff00000, ez = fm::hi32(Z) & 0x7ff00000;
+            const bool bad_coord = ty | ((ex > ez ? ex : ez) < 0x21f00000);
             double acc[1] = {0.0};
-            node_eval<MASK>(acc, X, Y, Z, fm::add(fm::mul(X, X), YY), tx & ty, tx | ty, u0, u1, u2, f, sh);
-            if (e < slab) cur[e] = acc[0];
-            e += step;
-            ia += dr;
-            c += dq;
-            if (ia >= nxp) { ia -= nxp; ++c; }
+            const NodePrims np = node_prims<MASK>(X, Y, Z, fm::add(fm::mul(X, X), YY), bad_coord, sh, tb);
+            node_add<MASK>(acc, np, X, Y, Z, u0, u1, u2, f);
+            if (ea < e_end) fm::sts_f64(ea, acc[0]);
+            ea += step_b;
+            xa += dr_b;
+            za += dq_b;
+            if (xa >= xs_end) { xa -= row_b; za += 8u; }
         }
         __syncthreads();
         // ---- the cells between node rows b-1 and b ----
@@ -110,23 +126,23 @@ __global__ void __launch_bounds__(MJ_THREADS) mesh_jacobian_kernel(const MeshJac
             const int j = b - 1;
             const int64_t kstride = (int64_t)ny * nx * (TRANSPOSED ? ld : 1);
             for (int i = sub * 32 + lane; i < nx; i += step) {
-                const double *cp = cur + i, *pp = prev + i;
+                unsigned ca = cur + 8u * (unsigned)i, pa = prev + 8u * (unsigned)i;
                 double *dst = TRANSPOSED ? row_base + ((int64_t)j * nx + i) * ld
                                          : row_base + ((int64_t)j * nx + i);
-                double below = (cp[1] - cp[0]) - (pp[1] - pp[0]);
+                double below = (fm::lds_f64_v8(ca) - fm::lds_f64_v(ca)) - (fm::lds_f64_v8(pa) - fm::lds_f64_v(pa));
 #pragma unroll 4
                 for (int k = 0; k < nz; ++k) {
-                    cp += nxp;
-                    pp += nxp;
-                    const double above = (cp[1] - cp[0]) - (pp[1] - pp[0]);
-                    __stcs(dst, (above - below) * scale);
+                    ca += row_b;
+                    pa += row_b;
+                    const double above = (fm::lds_f64_v8(ca) - fm::lds_f64_v(ca)) - (fm::lds_f64_v8(pa) - fm::lds_f64_v(pa));
+                    __stcs(dst, above - below);
                     dst += kstride;
                     below = above;
                 }
             }
         }
         __syncthreads();
-        double *t = cur; cur = prev; prev = t;
+        const unsigned t = cur; cur = prev; prev = t;
     }
 }
 

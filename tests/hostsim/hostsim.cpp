@@ -70,8 +70,8 @@ static void run_mesh(const double *xp, const double *yp, const double *zp, size_
                 for (int c = 0; c < nzp; ++c, ++g) {
                     const double w0 = w[0][g], w1 = MAG ? w[1][g] : 0.0, w2 = MAG ? w[2][g] : 0.0;
                     if (w0 == 0.0 && w1 == 0.0 && w2 == 0.0) continue;
-                    node_eval<MASK>(acc, X, Y, zn[c] - zp[l], sxy, below_2m480(X) & below_2m480(Y),
-                                    below_2m480(X) | below_2m480(Y), w0, w1, w2, fv, sh);
+                    node_eval<MASK>(acc, X, Y, zn[c] - zp[l], sxy, column_bits(X, Y), w0, w1, w2, fv, sh,
+                                    fm::tab_ref());
                 }
             }
         for (int c = 0; c < NC; ++c) out[(size_t)c * n + l] = acc[c];
