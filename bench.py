@@ -2,7 +2,7 @@
 """
 Benchmark of the prism forward model on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5|c5t|...]
     python bench.py --impl reference ...          # the reference's CPU path, same metric
 
 Metric (BASELINE.json): prism x point evaluations per second, fp64.  One "step" is
@@ -16,19 +16,23 @@ data-path collective); value = all pairs of all ranks / max-over-ranks device ti
              from CUDA events on the library's own stream, summed over the K steps.
   e2e      : the public Python API (prism.fields) with HOST numpy arrays: mesh
              flattening, model upload, point H2D, kernels, result D2H, every step.
-  evaluation : regular PrismMesh models (C2, C3) are evaluated once per mesh NODE
-             (csrc/prism_mesh.cuh); --per-cell forces the general per-cell kernels.
-  roofline : FP64 pipe.  achieved = pairs/s x F, F = SURVEY 8(d)'s fused-minimal FLOP
-             per pair of the REFERENCE formulation (what the answer costs with
-             libdevice-grade log/atan2 per corner); peak = DFMA-chain rate measured
-             in this run (MEASURED_PEAKS.json has no FP64 figure).  The kernel uses
-             an algebraically collapsed formulation with fewer instructions, so
-             achieved/peak can exceed 1; "executed_frac" is the real FP64-pipe
-             utilisation = executed FP64 instr/pair (ncu, profiles/) x pairs/s / issue rate.
+  roofline : FP64 pipe.  achieved = FP64-pipe instruction slots the dominant kernel EXECUTES
+             per pair (ncu smsp__inst_executed_pipe_fp64, read from profiles/r02_kernel_*.json,
+             which carries the hash of csrc/ it was measured on; a stale file is refused)
+             x 2 x pairs/s; peak = the DFMA-chain rate measured in this run
+             (MEASURED_PEAKS.json has no FP64 figure); frac = achieved / peak = the measured
+             FP64-pipe utilisation.  "algorithmic" restates the same throughput in FLOP of the
+             REFERENCE formulation; it is not a fraction of anything.
+  configs  : the other BASELINE configs (C1 latency, C3, C4, C5, C5 gz+tensor), a few steps
+             each, in the same JSON line; "strong": a fixed slab of the north-star problem
+             (62 500 of the 1e6 points x 1e6 prisms, gz + tensor) split over the ranks.
   cpu_baseline : the reference's own Cython kernel (oracle/_ref, "reference") or the C
-             port ("port") on this box's host cores, on a bounded sample.
+             port ("port") on this box's host cores, on a bounded sample; "parity": the
+             worst excess of the GPU result over the stated tolerance on sampled points.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -45,34 +49,44 @@ METRIC = "prism_point_evals_per_s"
 UNIT = "pairs/s"
 
 # algorithmic work per prism x point pair of the reference
-# formulation fused into one pass (FLOP, DFMA = 2) and FP64-pipe slots.
+# formulation fused into one pass (FLOP, DFMA = 2).
 WORK = {
-    "c2": dict(flop=2802.0, slots=1922.0, what="6 tensor components"),
-    "c2a": dict(flop=2802.0, slots=1922.0, what="6 tensor components"),
-    "c3": dict(flop=2820.0, slots=1940.0, what="tf+bx+by+bz"),
-    "c4": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
-    "c5": dict(flop=1478.0, slots=1022.0, what="gz"),
-    "c5t": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
-    "c4full": dict(flop=1478.0, slots=1022.0, what="Jacobian gz (+8 B stored per entry)"),
-    "c5full": dict(flop=1478.0, slots=1022.0, what="gz"),
-    "c5tfull": dict(flop=2850.0, slots=1970.0, what="gz + 6 tensor components"),
+    "c1": dict(flop=1478.0, what="gz"),
+    "c2": dict(flop=2802.0, what="6 tensor components"),
+    "c2a": dict(flop=2802.0, what="6 tensor components"),
+    "c3": dict(flop=2820.0, what="tf+bx+by+bz"),
+    "c4": dict(flop=1478.0, what="Jacobian gz (+8 B stored per entry)"),
+    "c5": dict(flop=1478.0, what="gz"),
+    "c5t": dict(flop=2850.0, what="gz + 6 tensor components"),
+    "c4full": dict(flop=1478.0, what="Jacobian gz (+8 B stored per entry)"),
+    "c5full": dict(flop=1478.0, what="gz"),
+    "c5tfull": dict(flop=2850.0, what="gz + 6 tensor components"),
+    "c5tslab": dict(flop=2850.0, what="gz + 6 tensor components"),
 }
-# FP64-pipe instructions the fast kernels actually execute per pair (ncu
-# smsp__inst_executed_pipe_fp64 / pairs, see profiles/); None until measured.
-# c4: the Jacobian kernel runs the same pair evaluator as c5; the profiled first row block
-# executes 373 because 2/3 of its rows lie on mesh planes (careful variant), see profiles/.
-# DRAM traffic of the dominant kernel per launch (ncu dram__bytes_read.sum +
-# dram__bytes_write.sum, profiles/r01_*): the model and the points are read once, the
-# outputs (<= 2 MB) stay in L2 until the D2H copy.  Bytes per launch at the profiled size.
-DRAM_TRAFFIC_PER_LAUNCH = {"c2": 1.47e6, "c2a": 1.47e6, "c3": None, "c4": None, "c5": None, "c5t": None}
-EXECUTED_FP64_PER_PAIR = {"c2": 421.7, "c2a": 421.7, "c3": 441.8, "c4": 318.5, "c5": 318.5, "c5t": 523.3,
-                          "c5full": 318.5, "c5tfull": 523.3, "c4full": 318.5}   # profiles/r01_*
-# the same for the node-sharing kernel of regular meshes, per CELL x point pair
-# (profiles/r01_c2_tensor_nodes.txt, r01_c3_mag4_nodes.txt)
-EXECUTED_FP64_PER_PAIR_NODES = {"c2": 187.3, "c2a": 187.3, "c3": 205.8,
-                                "c4": 109.5, "c4full": 109.5}      # c4: profiles/r01_c4_jacobian_nodes.txt
-# and for the surface form of a relief (profiles/r01_c5_gz_surface.txt, r01_c5t_gz_tensor_surface.txt)
-EXECUTED_FP64_PER_PAIR_SURFACE = {"c5": 202.5, "c5t": 342.6, "c5full": 202.5, "c5tfull": 342.6}
+
+
+def csrc_hash():
+    """Hash of everything the CUDA library is built from (a profile is only valid for it)."""
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "fatiando_b200", "csrc", "*")) +
+                   glob.glob(os.path.join(ROOT, "include", "*.h")))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_profile(key):
+    """profiles/r02_kernel_<key>.json (tools/summarize_profile.py --json), or None when missing/stale."""
+    path = os.path.join(ROOT, "profiles", "r02_kernel_%s.json" % key)
+    try:
+        d = json.load(open(path))
+    except (OSError, ValueError):
+        return None, "no profiles/r02_kernel_%s.json" % key
+    if d.get("csrc_hash") != csrc_hash():
+        return None, "profiles/r02_kernel_%s.json is stale (measured on csrc %s, this build is %s)" % (
+            key, d.get("csrc_hash"), csrc_hash())
+    return d, os.path.relpath(path, ROOT)
 
 
 # --------------------------------------------------------------------------
@@ -82,6 +96,14 @@ def make_workload(name, world=1):
     from fatiando_b200 import mesher, gridder, utils
     from tools.synthetic import hill
     rs = np.random.RandomState
+    if name == "c1":
+        # cookbook/gravmag_grav_prism.py: gz of 3 prisms on a 100x100 grid (latency case)
+        model = [mesher.Prism(-4000, -3000, -4000, -3000, 0, 2000, {'density': 1000}),
+                 mesher.Prism(-1000, 1000, -1000, 1000, 0, 2000, {'density': -900}),
+                 mesher.Prism(2000, 4000, 3000, 4000, 0, 2000, {'density': 1300})]
+        xp, yp, zp = gridder.regular((-5000, 5000, -5000, 5000), (100, 100), z=-150)
+        return dict(model=model, prop='density', names=['gz'], xp=xp, yp=yp, zp=zp, fvec=None,
+                    kind='forward', label="C1: gz of 3 prisms on a 100x100 grid (cookbook)")
     if name == "c2":
         mesh = mesher.PrismMesh((0, 5000, 0, 5000, 0, 2000), (20, 50, 50))
         mesh.addprop('density', rs(0).uniform(-1000, 1000, mesh.size))
@@ -132,6 +154,16 @@ def make_workload(name, world=1):
         xp, yp, zp = gridder.regular((0, 10000, 0, 10000), (500, 500), z=-100)
         w['xp'], w['yp'], w['zp'] = xp, yp, zp
         w['label'] = "C4 full: gz sensitivity matrix, 250000 observations x 40000 PrismMesh cells (80 GB fp64), device-resident, row-sharded over the GPUs in use"
+        w['scaling'] = 'strong'
+        return w
+    if name == "c5tslab":
+        # a fixed slab of the north-star problem, the same at every N (strong scaling): every
+        # 16th of the 1e6 points x all 1e6 prisms, gz + tensor, points sharded over the ranks
+        w = make_workload("c5t", 1)
+        xp, yp, zp = gridder.regular((0, 1e6, 0, 1e6), (1000, 1000), z=-5000)
+        w['xp'], w['yp'], w['zp'] = xp[::16].copy(), yp[::16].copy(), zp[::16].copy()
+        w['label'] = ("C5 slab: gz+tensor of a 1000x1000 PrismRelief (1e6 prisms) at 62500 of the 1e6 "
+                      "points (every 16th), z=-5000; fixed total work, points sharded over the GPUs")
         w['scaling'] = 'strong'
         return w
     if name in ("c5full", "c5tfull"):
@@ -254,48 +286,103 @@ def _cpu_model():
     return "unknown"
 
 
-def cpu_baseline(w, flat, seconds=15.0, cores=None):
-    """pairs/s of the reference CPU path on a bounded sample of workload w."""
-    import multiprocessing as mp
-    from oracle import prism_oracle as po
-    cores = cores or os.cpu_count() or 1
-    m = flat.size
-    if w['prop'] == 'magnetization':
-        props = flat.magnetization
-    elif flat.density is not None:
-        props = flat.density[:, None]
-    else:
-        props = np.ones((m, 1))
-    bounds = flat.bounds
-    per_field_rate = 1.5e6       # pairs/s/core per field call, sizing only (BASELINE.md section 2)
-    pts_per_core = max(1, int(per_field_rate * seconds / (m * len(w['names']))))
-    n_s = min(w['xp'].size, pts_per_core * cores)
-    idx = np.linspace(0, w['xp'].size - 1, n_s).astype(np.int64)
-    xs, ys, zs = w['xp'][idx].copy(), w['yp'][idx].copy(), w['zp'][idx].copy()
-    edges = np.linspace(0, n_s, min(cores, n_s) + 1).astype(int)
-    jobs = [(w['names'], xs[a:b], ys[a:b], zs[a:b], bounds, props, w['fvec'], w['kind'])
-            for a, b in zip(edges[:-1], edges[1:]) if b > a]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(len(jobs)) as pool:
-        warm = [(j[0], j[1][:1], j[2][:1], j[3][:1]) + j[4:] for j in jobs]
-        pool.map(_cpu_chunk, warm)                  # import + page-in, one point per worker
+POINTS_PER_CALL = 64        # observation points per `_prism.<field>` call and worker (the reference
+                            # spends ~2 us per call in Python: below ~50 points that halves its rate)
+
+
+class CpuArm(object):
+    """
+    The reference CPU path on a bounded sample of a workload: every host core gets
+    POINTS_PER_CALL observation points and drives the reference's compiled kernel the way
+    prism.py:131-141 does (one call per prism and field), over a strided sample of the
+    prisms sized for `seconds` per step.  ONE pool of workers for all steps.
+    """
+
+    def __init__(self, w, flat, seconds, cores=None):
+        import multiprocessing as mp
+        from oracle import prism_oracle as po
+        self.kind = "reference" if po.ref_available() else "port"
+        cores = cores or os.cpu_count() or 1
+        m = flat.size
+        if w['prop'] == 'magnetization':
+            props = flat.magnetization
+        elif flat.density is not None:
+            props = flat.density[:, None]
+        else:
+            props = np.ones((m, 1))
+        per_field_rate = 1.3e6       # pairs/s/core per field call, sizing only (BASELINE.md section 2)
+        nf = len(w['names'])
+        pts = min(POINTS_PER_CALL, max(1, w['xp'].size // cores))
+        m_s = int(min(m, max(1000, per_field_rate * seconds / (pts * nf))))
+        sel = np.unique(np.linspace(0, m - 1, m_s).astype(np.int64))
+        bounds = [np.ascontiguousarray(b[sel]) for b in flat.bounds]
+        props = np.ascontiguousarray(props[sel])
+        n_s = min(w['xp'].size, pts * cores)
+        idx = np.linspace(0, w['xp'].size - 1, n_s).astype(np.int64)
+        xs, ys, zs = w['xp'][idx].copy(), w['yp'][idx].copy(), w['zp'][idx].copy()
+        edges = np.linspace(0, n_s, min(cores, n_s) + 1).astype(int)
+        self.jobs = [(w['names'], xs[a:b], ys[a:b], zs[a:b], bounds, props, w['fvec'], w['kind'])
+                     for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        self.pairs = float(n_s) * sel.size
+        self.what = ("%d of %d points (%d per worker and call) x %d of %d prisms, %d field call(s) per prism (%s)"
+                     % (n_s, w['xp'].size, self.jobs[0][1].size, sel.size, m, nf, '+'.join(w['names'])))
+        self.pool = mp.get_context("fork").Pool(len(self.jobs))
+        warm = [(j[0], j[1][:1], j[2][:1], j[3][:1], [bb[:8] for bb in j[4]], j[5][:8], j[6], j[7])
+                for j in self.jobs]
+        self.pool.map(_cpu_chunk, warm)            # import + page-in
+
+    def step(self):
         t0 = time.perf_counter()
-        pool.map(_cpu_chunk, jobs)
+        self.pool.map(_cpu_chunk, self.jobs)
+        return time.perf_counter() - t0
+
+    def one_core(self):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_chunk, self.jobs[:1])
         dt = time.perf_counter() - t0
-        # (i) of BASELINE.md section 3: one core, on one worker's share of the sample
-        t1 = time.perf_counter()
-        pool.map(_cpu_chunk, jobs[:1])
-        dt1 = time.perf_counter() - t1
-    pairs = float(n_s) * m
-    one_core = float(jobs[0][1].size) * m / dt1
-    return {"value": pairs / dt, "unit": UNIT, "cores": len(jobs),
-            "kind": "reference" if po.ref_available() else "port",
-            "cpu_model": _cpu_model(), "one_core_value": one_core,
-            "sample": "%d of %d points x all %d prisms, %d field call(s) each (%s), %.1f s on %d cores; "
-                      "one core: %d points, %.1f s" % (
-                          n_s, w['xp'].size, m, len(w['names']), '+'.join(w['names']), dt, len(jobs),
-                          jobs[0][1].size, dt1),
-            "seconds": dt}
+        return float(self.jobs[0][1].size) * self.jobs[0][4][0].size / dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, value, seconds, one_core=None):
+        return {"value": value, "unit": UNIT, "cores": len(self.jobs), "kind": self.kind,
+                "cpu_model": _cpu_model(), "one_core_value": one_core,
+                "sample": "%s; %.1f s per step on %d cores" % (self.what, seconds, len(self.jobs))}
+
+
+def cpu_baseline(w, flat, seconds=15.0):
+    arm = CpuArm(w, flat, seconds)
+    try:
+        dt = arm.step()
+        one = arm.one_core()
+    finally:
+        arm.close()
+    return arm.describe(arm.pairs / dt, dt, one)
+
+
+def parity_sample(w, flat, got, idx):
+    """
+    Worst excess of the GPU fields `got` (at the points idx of workload w) over the stated
+    tolerance 1e-9*|ref| + c*eps*A against the C restatement of the reference (oracle/, the
+    checker), c = 0.1 (tests/helpers.py).  <= 1 passes.
+    """
+    from oracle import prism_oracle as po
+    threads = os.cpu_count() or 1
+    xp, yp, zp = (np.ascontiguousarray(w[k][idx]) for k in ('xp', 'yp', 'zp'))
+    worst = 0.0
+    for f in w['names']:
+        if w['prop'] == 'magnetization':
+            pr = flat.magnetization if f != 'tf' else np.hstack([flat.magnetization,
+                                                                 np.tile(w['fvec'], (flat.size, 1))])
+        else:
+            pr = flat.density[:, None]
+        ref = po.model(f, xp, yp, zp, flat.bounds, pr, threads=threads)
+        cond = po.condition(f, xp, yp, zp, flat.bounds, pr, threads=threads)
+        tol = 1e-9 * np.abs(ref) + 0.1 * 2.0 ** -52 * cond
+        worst = max(worst, float(np.max(np.abs(got[f] - ref) / tol)))
+    return worst
 
 
 # --------------------------------------------------------------------------
@@ -313,213 +400,323 @@ def run_reference(args):
     from fatiando_b200.flatten import flatten
     w = make_workload(args.workload, 1)
     flat = flatten(w['model'], w['prop'], override=w['prop'] is None, fvec=w['fvec'])
-    steps = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_baseline(w, flat, seconds=max(2.0, 60.0 / (args.warmup + args.steps)))
-        if i >= args.warmup:
-            steps.append(r)
-    value = float(np.mean([s['value'] for s in steps]))
+    # the whole run within a few minutes: <= 10 s of CPU work per step, <= ~150 s in all
+    seconds = min(10.0, 150.0 / max(1, args.warmup + args.steps))
+    arm = CpuArm(w, flat, seconds)
+    try:
+        times = [arm.step() for _ in range(args.warmup + args.steps)][args.warmup:]
+        one = arm.one_core()
+    finally:
+        arm.close()
+    dt = float(np.mean(times))
+    value = arm.pairs / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * float(np.mean([s['seconds'] for s in steps])),
+            "ms_per_step": 1e3 * dt,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (seeded)", "config": {"workload": w['label']},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": steps[0]['cores'],
-                             "kind": steps[0]['kind'], "sample": steps[0]['sample'],
-                             "cpu_model": steps[0]['cpu_model'],
-                             "one_core_value": float(np.mean([s['one_core_value'] for s in steps]))},
+            "cpu_baseline": arm.describe(value, dt, one),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def run_gpu(args):
-    import torch
-    from fatiando_b200 import _lib, prism
-    from fatiando_b200.flatten import flatten
-    import ctypes
+# --------------------------------------------------------------------------
+# the GPU arm
+# --------------------------------------------------------------------------
+class Bench(object):
+    def __init__(self, args):
+        import torch
+        from fatiando_b200 import _lib, prism
+        self.torch, self._lib, self.prism = torch, _lib, prism
+        self.args = args
+        self.world, self.rank, self.local = dist_setup(args.gpus)
+        prism.NODE_SHARING = not args.per_cell          # the e2e leg goes through prism.fields
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        _lib.require_device()
+        self.dev = self.local
+        self.tdev = torch.device("cuda", self.dev)
+        self.lib = _lib.lib()
+        self.models = {}
 
-    world, rank, local = dist_setup(args.gpus)
-    prism.NODE_SHARING = not args.per_cell          # the e2e leg goes through prism.fields
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.require_device()
-    dev = local
-    lib = _lib.lib()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    w = make_workload(args.workload, world)
-    from fatiando_b200.partition import local_slice
-    sl = local_slice(w['xp'].size, rank, world)
-    xp, yp, zp = (np.ascontiguousarray(a[sl]) for a in (w['xp'], w['yp'], w['zp']))
-    n = xp.size
-    flat = flatten(w['model'], w['prop'], override=w['prop'] is None, fvec=w['fvec'])
-    m = flat.size
-    names = w['names']
-    ncomp = len(names)
-    # hand the mesh object itself over, so that a regular PrismMesh also gets its
-    # node-sharing form (the per-cell arrays are uploaded either way)
-    model = prism.Model(w['model'], w['prop'], keep_all=w['prop'] is None, fvec=w['fvec'], device=dev,
-                        node_sharing=not args.per_cell)
-    tdev = torch.device("cuda", dev)
-    d_pts = [torch.from_numpy(a).to(tdev) for a in (xp, yp, zp)]
-    ids = sorted(_lib.FIELD_ID[nm] for nm in names)
-    mask = sum(1 << i for i in ids)
-    scale = np.array([prism.unit_scale(_lib.FIELDS[i]) for i in ids])
-    fvec = None if w['fvec'] is None else np.ascontiguousarray(w['fvec'], dtype=np.float64)
-    if w['kind'] == 'jacobian':
-        d_out = torch.empty((n, m), dtype=torch.float64, device=tdev)
-    else:
-        d_out = torch.empty((ncomp, n), dtype=torch.float64, device=tdev)
-    unit = np.array([1.0])
-    torch.cuda.synchronize()
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.tdev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return t.tolist()
 
-    def step_device():
-        if w['kind'] == 'jacobian':
-            rc = lib.fb200_jacobian(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
-                                    d_pts[2].data_ptr(), n, ids[0], _lib.dptr(unit), _lib.dptr(fvec),
-                                    float(scale[0]), d_out.data_ptr(), m, _lib.DEVICE_POINTERS)
-        else:
-            rc = lib.fb200_forward(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
-                                   d_pts[2].data_ptr(), n, mask, None, None, _lib.dptr(fvec),
-                                   _lib.dptr(scale), d_out.data_ptr(), n, _lib.DEVICE_POINTERS)
-        _lib.check(rc)
-        return model.last_kernel_ms()
+    def model_of(self, w, key):
+        """One resident model per distinct mesh (C5, C5t and the strong slab share theirs)."""
+        if key not in self.models:
+            from fatiando_b200.flatten import flatten
+            flat = flatten(w['model'], w['prop'], override=w['prop'] is None, fvec=w['fvec'])
+            model = self.prism.Model(flat, w['prop'], keep_all=w['prop'] is None, fvec=w['fvec'],
+                                     device=self.dev, node_sharing=not self.args.per_cell)
+            self.models[key] = (model, flat)
+        return self.models[key]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def evaluation(self, model, w):
+        if model.nodes is not None:
+            return "nodes"
+        if model.surface is not None and w['kind'] == 'forward':
+            return "surface"
+        return "cells"
+
+    def measure(self, name, steps, warmup, weak=True, e2e_steps=0, clocks=False, model_key=None):
+        """Time `steps` passes over workload `name`; returns a dict (identical on all ranks)."""
+        torch, _lib, lib, prism = self.torch, self._lib, self.lib, self.prism
+        from fatiando_b200.partition import local_slice
+        w = make_workload(name, self.world if weak else 1)
+        sl = local_slice(w['xp'].size, self.rank, self.world)
+        xp, yp, zp = (np.ascontiguousarray(a[sl]) for a in (w['xp'], w['yp'], w['zp']))
+        n = xp.size
+        model, flat = self.model_of(w, model_key or name)
+        m = flat.size
+        names = w['names']
+        d_pts = [torch.from_numpy(a).to(self.tdev) for a in (xp, yp, zp)]
+        ids = sorted(_lib.FIELD_ID[nm] for nm in names)
+        mask = 0
+        for i in ids:
+            mask |= 1 << i
+        scale = np.array([prism.unit_scale(_lib.FIELDS[i]) for i in ids])
+        fvec = None if w['fvec'] is None else np.ascontiguousarray(w['fvec'], dtype=np.float64)
+        shape = (n, m) if w['kind'] == 'jacobian' else (len(names), n)
+        d_out = torch.empty(shape, dtype=torch.float64, device=self.tdev)
+        unit = np.array([1.0])
         torch.cuda.synchronize()
 
-    # the clock sampler needs ~0.1 s to produce its first line: start it before the warm-up
-    # (same load) so that short timed regions are covered too
-    sampler = ClockSampler(dev)
-    sampler.start()
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler.mark()
-    dev_ms, launches = 0.0, 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _lib.check(lib.fb200_flush_l2(dev))        # L2 hygiene, outside the step's events
-        ms, nl = step_device()
-        dev_ms += ms
-        launches += nl
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+        def step_device():
+            if w['kind'] == 'jacobian':
+                rc = lib.fb200_jacobian(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
+                                        d_pts[2].data_ptr(), n, ids[0], _lib.dptr(unit), _lib.dptr(fvec),
+                                        float(scale[0]), d_out.data_ptr(), m, _lib.DEVICE_POINTERS)
+            else:
+                rc = lib.fb200_forward(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
+                                       d_pts[2].data_ptr(), n, mask, None, None, _lib.dptr(fvec),
+                                       _lib.dptr(scale), d_out.data_ptr(), n, _lib.DEVICE_POINTERS)
+            _lib.check(rc)
+            return model.last_kernel_ms()
 
-    # ---- e2e: public API, host buffers, everything inside the timed region ----
-    def step_e2e():
-        if w['kind'] == 'jacobian':
-            rows = min(n, 2048)      # host-resident J is PCIe-bound: bounded row block
-            j = prism.jacobian(xp[:rows], yp[:rows], zp[:rows], w['model'], names[0], device=dev)
-            return rows, j.nbytes
-        res = prism.fields(xp, yp, zp, w['model'], names, inc=w.get('inc'), dec=w.get('dec'),
-                           device=dev)
-        return n, sum(v.nbytes for v in res.values())
-    if args.no_e2e:
+        sampler = None
+        if clocks:
+            # the sampler needs ~0.1 s to produce its first line: start it before the warm-up
+            sampler = ClockSampler(self.dev)
+            sampler.start()
+        for _ in range(max(warmup, 3)):               # timing rule: at least 3 warm-up steps
+            step_device()
+        self.barrier()
+        if sampler:
+            sampler.mark()
+        dev_ms, launches = 0.0, 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _lib.check(lib.fb200_flush_l2(self.dev))        # L2 hygiene, outside the step's events
+            ms, nl = step_device()
+            dev_ms += ms
+            launches += nl
+        self.barrier()
+        wall = time.perf_counter() - t0
+        res = {"name": name, "w": w, "flat": flat, "model": model, "local_points": (xp, yp, zp),
+               "clocks": sampler.stop() if sampler else None}
+
+        # ---- e2e: public API, host buffers, everything inside the timed region ----
         rows_done, d2h, e2e_s = n, 0, float('inf')
-    else:
-        step_e2e()
-        barrier()
-        t1 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
-        for _ in range(e2e_steps):
-            rows_done, d2h = step_e2e()
-        barrier()
-        e2e_s = (time.perf_counter() - t1) / e2e_steps
-    h2d = (6 + (3 if w['prop'] == 'magnetization' else (1 if w['prop'] else 0))) * m * 8 + 3 * rows_done * 8
-    # the merged forms are uploaded with the model every e2e step as well
-    if model.nodes is not None:
-        h2d += sum(a.nbytes for a in model.nodes.weights) + (model.nodes.xn.nbytes + model.nodes.yn.nbytes
-                                                             + model.nodes.zn.nbytes)
-    if model.surface is not None:
-        h2d += sum(a.nbytes for a in model.surface.faces) + sum(a.nbytes for a in model.surface.nodes)
+        if e2e_steps:
+            def step_e2e():
+                if w['kind'] == 'jacobian':
+                    rows = min(n, 4096)      # host-resident J is PCIe-bound: bounded row block
+                    j = prism.jacobian(xp[:rows], yp[:rows], zp[:rows], w['model'], names[0], device=self.dev)
+                    return rows, j.nbytes
+                r = prism.fields(xp, yp, zp, w['model'], names, inc=w.get('inc'), dec=w.get('dec'),
+                                 device=self.dev)
+                return n, sum(v.nbytes for v in r.values())
+            step_e2e()
+            self.barrier()
+            t1 = time.perf_counter()
+            for _ in range(e2e_steps):
+                rows_done, d2h = step_e2e()
+            self.barrier()
+            e2e_s = (time.perf_counter() - t1) / e2e_steps
+        h2d = (6 + (3 if w['prop'] == 'magnetization' else (1 if w['prop'] else 0))) * m * 8 + 3 * rows_done * 8
+        # the merged forms are uploaded with the model every e2e step as well
+        if model.nodes is not None:
+            h2d += sum(a.nbytes for a in model.nodes.weights) + (model.nodes.xn.nbytes + model.nodes.yn.nbytes
+                                                                 + model.nodes.zn.nbytes)
+        if model.surface is not None:
+            h2d += sum(a.nbytes for a in model.surface.faces) + sum(a.nbytes for a in model.surface.nodes)
 
-    # ---- reduce over ranks: max time, summed work ----
-    stats = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device=tdev)
-    work = torch.tensor([float(n) * m, float(rows_done) * m, float(launches)], dtype=torch.float64, device=tdev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_max, wall_max = stats.tolist()
-    pairs_step, pairs_e2e, launches_all = work.tolist()
-    ms_per_step = dev_ms_max / args.steps
-    value = pairs_step / (ms_per_step * 1e-3)
+        # ---- over ranks: max time, summed work ----
+        dev_ms_max, e2e_max, wall_max = self.reduce([dev_ms, e2e_s, wall], "MAX")
+        pairs_step, pairs_e2e, launches_all = self.reduce([float(n) * m, float(rows_done) * m, float(launches)], "SUM")
+        ms_per_step = dev_ms_max / steps
+        res.update(value=pairs_step / (ms_per_step * 1e-3), ms_per_step=ms_per_step, steps=steps,
+                   pairs_per_step=pairs_step, wall_ms_per_step=1e3 * wall_max / steps,
+                   gpu_launches=int(launches_all), evaluation=self.evaluation(model, w),
+                   e2e=None if not e2e_steps else {
+                       "value": pairs_e2e / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h),
+                       "api": "fatiando_b200.prism (flatten + upload + H2D + kernels + D2H per step)"})
+        del d_out
+        return res
+
+    def fp64_peak(self):
+        import ctypes
+        burst, sustained = ctypes.c_double(0), ctypes.c_double(0)
+        self._lib.check(self.lib.fb200_fp64_peak(self.dev, 1.0, ctypes.byref(burst), ctypes.byref(sustained)))
+        return burst.value, sustained.value
+
+    def roofline(self, res, peaks, brief=False):
+        """FP64-pipe roofline of the dominant kernel of a measured workload (rank 0)."""
+        name, w = res['name'], res['w']
+        base = {"c2a": "c2", "c4full": "c4", "c5full": "c5", "c5tfull": "c5t", "c5tslab": "c5t"}.get(name, name)
+        prof, src = load_profile("%s_%s" % (base, res['evaluation']))
+        per_gpu = res['value'] / self.world
+        peak = peaks[1] if res['ms_per_step'] > 500 else peaks[0]
+        wk = WORK[name]
+        out = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak, "profile": src}
+        if prof:
+            executed = prof["fp64_inst_per_pair"]
+            out.update(achieved=per_gpu * executed * 2.0 / 1e12, frac=per_gpu * executed * 2.0 / 1e12 / peak,
+                       executed_fp64_inst_per_pair=executed, executed_inst_per_pair=prof.get("inst_per_pair"),
+                       kernel=prof.get("kernel"), traffic=prof.get("dram_bytes_per_launch"),
+                       ncu_pipe_fp64_pct=prof.get("pipe_fp64_pct"))
+        else:
+            out.update(achieved=None, frac=None, traffic=None)
+        out["algorithmic"] = {"flop_per_pair": wk['flop'], "of": wk['what'],
+                              "equivalent_tflops": per_gpu * wk['flop'] / 1e12}
+        if not brief:
+            out["peak_source"] = ("DFMA-chain microbenchmark in this run (fb200_fp64_peak: burst %.2f, sustained "
+                                  "%.2f TFLOP/s; the sustained figure for steps longer than 0.5 s); "
+                                  "MEASURED_PEAKS.json has no FP64 figure" % peaks)
+            out["note"] = ("achieved = FP64-pipe instruction slots the kernel EXECUTES per pair (ncu, the "
+                           "profiles/ file named above, valid for this build's csrc hash only) x 2 x pairs/s; "
+                           "frac = FP64-pipe utilisation.  algorithmic = pairs/s x FLOP per pair of the "
+                           "REFERENCE formulation (libm-grade log/atan2 per corner, SURVEY 8(d)): a speed-up "
+                           "figure that exceeds the FP64 peak, not a roofline fraction")
+        if w['kind'] == 'jacobian':
+            peaks_file = {}
+            try:
+                peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm = peaks_file.get("hbm_gbs", 6650.0)
+            out["hbm_write"] = {"achieved_gbs": per_gpu * 8 / 1e9, "peak_gbs": hbm,
+                                "frac": per_gpu * 8 / 1e9 / hbm,
+                                "peak_source": "MEASURED_PEAKS.json" if peaks_file else "fallback"}
+        return out
+
+    def latency_c1(self):
+        """C1 (parity + latency only): the cookbook call through the public API."""
+        prism = self.prism
+        w = make_workload("c1", 1)
+        xp, yp, zp = w['xp'], w['yp'], w['zp']
+
+        def med(fn, reps=30):
+            fn()
+            t = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                t.append(time.perf_counter() - t0)
+            return 1e3 * float(np.median(t))
+        out = {"workload": w['label'],
+               "prism.gz_ms": med(lambda: prism.gz(xp, yp, zp, w['model'])),
+               "prism.fields_10_ms": med(lambda: prism.fields(xp, yp, zp, w['model'], list(prism.GRAVITY_FIELDS)))}
+        with prism.Model(w['model'], 'density', device=self.dev) as model:
+            out["Model.fields_gz_resident_ms"] = med(lambda: model.fields(xp, yp, zp, ['gz']))
+            out["kernel_ms"] = model.last_kernel_ms()[0]
+        out["note"] = "median of 30 calls with host numpy buffers (flatten + upload + H2D + kernel + D2H)"
+        return out
+
+    def close(self):
+        for model, _ in self.models.values():
+            model.close()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def run_gpu(args):
+    B = Bench(args)
+    world, rank = B.world, B.rank
+    main = B.measure(args.workload, args.steps, args.warmup, weak=not args.workload.endswith(("full", "slab")),
+                     e2e_steps=0 if args.no_e2e else max(1, min(args.steps, 3)), clocks=True)
+    extra = {}
+    strong = None
+    if args.workload == "c2" and not args.no_configs:
+        for name in ("c3", "c4", "c5", "c5t"):
+            extra[name] = B.measure(name, 3, 3, weak=True, e2e_steps=0,
+                                    model_key="c5" if name.startswith("c5") else name)
+        strong = B.measure("c5tslab", 2, 3, weak=False, model_key="c5")
 
     line = None
     if rank == 0:
-        wk = WORK[args.workload]
-        burst, sustained = ctypes.c_double(0), ctypes.c_double(0)
-        _lib.check(lib.fb200_fp64_peak(dev, 1.0, ctypes.byref(burst), ctypes.byref(sustained)))
-        per_gpu = value / world
-        achieved = per_gpu * wk['flop'] / 1e12
-        peak = sustained.value if ms_per_step > 500 else burst.value
-        executed = (EXECUTED_FP64_PER_PAIR_NODES if model.nodes is not None
-                    else EXECUTED_FP64_PER_PAIR_SURFACE if model.surface is not None and w['kind'] == 'forward'
-                    else EXECUTED_FP64_PER_PAIR).get(args.workload)
-        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak if peak else None,
-                    "traffic": DRAM_TRAFFIC_PER_LAUNCH.get(args.workload),
-                    "peak_source": "DFMA-chain microbenchmark in this run (fb200_fp64_peak: burst %.2f, "
-                                   "sustained %.2f TFLOP/s); MEASURED_PEAKS.json has no FP64 figure"
-                                   % (burst.value, sustained.value),
-                    "algorithmic_flop_per_pair": wk['flop'], "algorithmic_of": wk['what'],
-                    "note": "achieved = pairs/s x F with F = SURVEY 8(d)'s FLOP per pair of the reference "
-                            "formulation (libm-grade log/atan2 per corner); the kernels reach the same "
-                            "answer with collapsed sums / node sharing in ~190-520 FP64 instructions per "
-                            "pair, so frac exceeds 1; executed_frac = executed FP64-pipe instructions "
-                            "(ncu, profiles/) x pairs/s / (148 SM x 64 lanes x clock) is the measured "
-                            "FP64-pipe utilisation",
-                    "executed_fp64_inst_per_pair": executed,
-                    "executed_frac": (per_gpu * executed / (148 * 64 * sm_hz)
-                                      if executed else None)}
-        if w['kind'] == 'jacobian':
-            peaks = {}
-            try:
-                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            except Exception:
-                pass
-            hbm = peaks.get("hbm_gbs", 6650.0)
-            roofline["hbm_write"] = {"achieved_gbs": per_gpu * 8 / 1e9, "peak_gbs": hbm,
-                                     "frac": per_gpu * 8 / 1e9 / hbm,
-                                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            w1 = make_workload(args.workload, 1)
-            cpu = cpu_baseline(w1, flat, seconds=15.0)
-            cpu.pop("seconds", None)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        peaks = B.fp64_peak()
+        w = main['w']
+
+        def brief(res):
+            return {"workload": res['w']['label'], "value": res['value'], "unit": UNIT,
+                    "ms_per_step": res['ms_per_step'], "steps": res['steps'], "warmup": 3,
+                    "pairs_per_step": res['pairs_per_step'], "evaluation": res['evaluation'],
+                    "gpu_launches": res['gpu_launches'], "roofline": B.roofline(res, peaks, brief=True)}
+        configs = {k: brief(v) for k, v in extra.items()}
+        if extra:
+            configs["c1"] = B.latency_c1()
+        cpu, parity = None, None
+        if not args.no_cpu:
+            cpu = cpu_baseline(make_workload(args.workload, 1), main['flat'], seconds=10.0)
+            if world == 1 and main['w']['kind'] == 'forward':
+                parity = {"tolerance": "|gpu - ref| <= 1e-9*|ref| + 0.1*eps*A (A = sum of absolute terms, "
+                                       "tests/helpers.py); excess <= 1 passes; 8 sampled points per config, "
+                                       "all prisms, every field, against the C restatement of the reference"}
+                for res in [main] + [extra[k] for k in ("c3", "c5t") if k in extra]:
+                    xp, yp, zp = res['local_points']
+                    idx = np.linspace(0, xp.size - 1, 8).astype(np.int64)
+                    got = res['model'].fields(np.ascontiguousarray(xp[idx]), np.ascontiguousarray(yp[idx]),
+                                              np.ascontiguousarray(zp[idx]), res['w']['names'], fvec=res['w']['fvec'])
+                    ww = dict(res['w'], xp=xp, yp=yp, zp=zp)
+                    parity[res['name']] = parity_sample(ww, res['flat'], got, idx)
+        evaluation = {"nodes": "node-sharing (regular mesh: one kernel evaluation per node)"
+                      if w['kind'] == 'forward' else
+                      "node-sharing Jacobian (one kernel evaluation per point and node, entries = signed "
+                      "sums of eight node values)",
+                      "surface": "surface form (relief: top faces + merged reference-plane nodes)",
+                      "cells": "per cell"}[main['evaluation']]
+        line = {"metric": METRIC, "value": main['value'], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main['ms_per_step'],
                 "higher_is_better": True, "scaling": w.get('scaling', 'weak'), "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic (seeded numpy RandomState)",
-                "config": {"workload": w['label'], "pairs_per_step": pairs_step,
-                           "fields": names, "parallelism": "obs-shard x%d" % world,
-                           "evaluation": ("node-sharing (regular mesh: one kernel evaluation per node)"
-                                          if model.nodes is not None and w['kind'] == 'forward' else
-                                          "node-sharing Jacobian (one kernel evaluation per point and node, "
-                                          "entries = signed sums of eight node values)"
-                                          if model.nodes is not None else
-                                          "surface form (relief: top faces + merged reference-plane nodes)"
-                                          if model.surface is not None and w['kind'] == 'forward' else
-                                          "per cell"),
+                "config": {"workload": w['label'], "pairs_per_step": main['pairs_per_step'],
+                           "fields": w['names'], "parallelism": "obs-shard x%d" % world,
+                           "evaluation": evaluation,
                            "l2": "flushed between steps (256 MiB memset); inputs (<4 MB) are "
                                  "smem/L2-resident by design, kernel is FP64-bound"},
-                "wall_ms_per_step": 1e3 * wall_max / args.steps,
-                "e2e": {"value": pairs_e2e / e2e_max, "unit": UNIT,
-                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "api": "fatiando_b200.prism (flatten + upload + H2D + kernels + D2H per step)"},
-                "gpu_launches": int(launches_all),
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "wall_ms_per_step": main['wall_ms_per_step'],
+                "e2e": main['e2e'], "gpu_launches": main['gpu_launches'],
+                "clocks": main['clocks'], "roofline": B.roofline(main, peaks), "cpu_baseline": cpu}
+        if configs:
+            line["configs"] = configs
+        if strong is not None:
+            s = brief(strong)
+            s["scaling"] = "strong"
+            s["note"] = ("the same 62500 x 1e6 slab at every N: value(N)/value(1) is the strong-scaling curve; "
+                         "the full 1e6 x 1e6 problem is 16 slabs (seconds = 16 x ms_per_step / 1000)")
+            s["north_star_seconds_at_this_n"] = 16.0 * strong['ms_per_step'] / 1e3
+            line["strong"] = s
+        if parity:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
-    model.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    B.close()
 
 
 def main():
@@ -531,11 +728,11 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORK))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (huge workloads)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="default workload only: skip the other BASELINE configs and the strong slab")
     ap.add_argument("--per-cell", action="store_true",
                     help="evaluate regular meshes cell by cell (no node sharing)")
     args = ap.parse_args()
-    if args.impl == "b200" and not args.workload.endswith("full"):
-        args.warmup = max(args.warmup, 3)       # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
     else:

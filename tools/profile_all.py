@@ -1,0 +1,71 @@
+"""
+One command per side for the profiles bench.py's roofline depends on.
+
+On the GPU box (under gpurun, one GPU):
+    python tools/profile_all.py gpu [keys...]
+        one `ncu --set full --clock-control none --import-source on` capture of the dominant
+        kernel of each workload -> gpurun_out/r02_<key>.ncu-rep, plus gpurun_out/r02_csrc_hash.txt
+        (the hash of the snapshot's csrc/, what the captures are valid for).
+
+Here, afterwards:
+    python tools/profile_all.py collect [keys...]
+        text summary + profiles/r02_kernel_<key>.json for each capture that came back.
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# key: (workload, extra profile_case args, ncu kernel regex, pairs per launch, title)
+CASES = {
+    "c2_nodes": ("c2", [], "mesh_forward", 4e4 * 5e4,
+                 "C2 six tensor components, node-sharing kernel mesh_forward_kernel<0x3F0>, 200x200 points x 50x50x20 mesh"),
+    "c3_nodes": ("c3", [], "mesh_forward", 2.5e5 * 1e5,
+                 "C3 tf+bx+by+bz, node-sharing kernel mesh_forward_kernel<0x3C00>, 500x500 points x 100x100x10 mesh"),
+    "c4_nodes": ("c4", ["--rows", "8192"], "mesh_jacobian", 8192 * 4e4,
+                 "C4 Jacobian gz, node-sharing kernel mesh_jacobian_kernel<0x008>, 8192 rows x 40000 cells"),
+    "c5_surface": ("c5", [], "forward_kernel", 15625 * 1e6,
+                   "C5 gz, relief surface form forward_kernel<0x008,EvalFace>, 15625 points x 1e6 top faces"),
+    "c5t_surface": ("c5t", [], "forward_kernel", 15625 * 1e6,
+                    "C5 gz+tensor, relief surface form forward_kernel<0x3F8,EvalFace>, 15625 points x 1e6 top faces"),
+    "c2_cells": ("c2", ["--per-cell"], "forward_kernel", 4e4 * 5e4,
+                 "C2 six tensor components, general per-cell kernel forward_kernel<0x3F0,EvalFast>"),
+    "c1_cells": ("c1", [], "forward_kernel", 1e4 * 3,
+                 "C1 gz of 3 prisms x 100x100 points, per-cell kernel forward_kernel<0x008,EvalFast>"),
+}
+
+
+def gpu(keys):
+    import bench
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    open(os.path.join(out, "r02_csrc_hash.txt"), "w").write(bench.csrc_hash())
+    for key in keys:
+        wl, extra, regex, _, _ = CASES[key]
+        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
+               "-k", "regex:" + regex, "-c", "1", "-f", "-o", os.path.join(out, "r02_" + key),
+               sys.executable, os.path.join(ROOT, "tools", "profile_case.py"), wl, "1"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        print(key, "rc", r.returncode, (r.stdout + r.stderr).strip().splitlines()[-1:])
+
+
+def collect(keys):
+    out = os.path.join(ROOT, "gpurun_out")
+    hashfile = os.path.join(out, "r02_csrc_hash.txt")
+    for key in keys:
+        rep = os.path.join(out, "r02_%s.ncu-rep" % key)
+        if not os.path.exists(rep):
+            print("missing", rep)
+            continue
+        _, _, _, pairs, title = CASES[key]
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "summarize_profile.py"), rep,
+                               os.path.join(ROOT, "profiles", "r02_%s.txt" % key), repr(float(pairs)), title,
+                               key, hashfile])
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else ""
+    keys = sys.argv[2:] or list(CASES)
+    {"gpu": gpu, "collect": collect}[mode](keys)

@@ -1,8 +1,16 @@
 """
 Write the judged summary of an ncu report into profiles/ (text, committed).
 
-    python tools/summarize_profile.py gpurun_out/prof_c2.ncu-rep profiles/r01_c2_tensor.txt PAIRS "title"
+    python tools/summarize_profile.py gpurun_out/prof_c2.ncu-rep profiles/r01_c2_tensor.txt PAIRS "title" [KEY [HASHFILE]]
+
+With KEY it also writes profiles/r02_kernel_KEY.json, the numbers bench.py's roofline reads
+(executed FP64-pipe instructions per pair, DRAM bytes per launch, ...) together with the hash
+of csrc/ the capture was taken on (HASHFILE = the hash the GPU box computed from its snapshot,
+default: this tree's); bench.py refuses the file when the hash differs from its build's.
 """
+import json
+import os
+import re
 import csv
 import io
 import subprocess
@@ -26,7 +34,7 @@ KEYS = [
 ]
 
 
-def main(rep, out, pairs, title):
+def main(rep, out, pairs, title, key=None, hashfile=None):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -45,7 +53,34 @@ def main(rep, out, pairs, title):
     lines += ['', '# dynamic instruction mix (ncu source page, executed warp instructions)', mix]
     open(out, 'w').write('\n'.join(lines))
     print('wrote', out)
+    if key:
+        def val(k):
+            return float(vals[hdr.index(k)].replace(',', '')) if k in hdr else None
+
+        def byts(k):
+            if k not in hdr:
+                return None
+            mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}[units[hdr.index(k)]]
+            return val(k) * mult
+        m = re.search(r'per pair: total ([0-9.]+)\s+fp64 ([0-9.]+)', mix)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        import bench
+        h = open(hashfile).read().strip() if hashfile else bench.csrc_hash()
+        d = {"key": key, "kernel": name, "pairs_per_launch": float(pairs),
+             "inst_per_pair": float(m.group(1)), "fp64_inst_per_pair": float(m.group(2)),
+             "time_ms": val('gpu__time_duration.sum'),
+             "pipe_fp64_pct": val('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed'),
+             "issue_active_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+             "dram_bytes_per_launch": (byts('dram__bytes_read.sum') or 0) + (byts('dram__bytes_write.sum') or 0),
+             "registers": val('launch__registers_per_thread'),
+             "csrc_hash": h, "source": os.path.basename(rep),
+             "how": "ncu --set full --clock-control none --import-source on, one launch; instruction "
+                    "counts from the source page (executed warp instructions x 32 / pairs)"}
+        path = os.path.join(root, 'profiles', 'r02_kernel_%s.json' % key)
+        json.dump(d, open(path, 'w'), indent=1)
+        print('wrote', path)
 
 
 if __name__ == '__main__':
-    main(*sys.argv[1:5])
+    main(*sys.argv[1:7])
