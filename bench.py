@@ -638,12 +638,62 @@ class Bench(object):
         out["note"] = "median of 30 calls with host numpy buffers (flatten + upload + H2D + kernel + D2H)"
         return out
 
+    def prism_shard(self, steps=3, npoints=10000):
+        """
+        The optional prism-sharded mode (north star): few points x a huge model.
+        10^4 points x the 10^6-prism relief, gz: every rank evaluates its contiguous 1/N of the
+        PRISMS at all points into a GPU tensor, ONE NCCL all-reduce adds the partial fields in
+        HBM (partition.PrismShards).  Device times: kernel on the library's stream, collective
+        on torch's stream (CUDA events), max over ranks.
+        """
+        from fatiando_b200 import partition
+        if self.dist is None:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29533")
+                self.torch.cuda.set_device(self.local)
+                dist.init_process_group("nccl", rank=0, world_size=1,
+                                        device_id=self.torch.device("cuda", self.local))
+                self._own_group = dist
+        w = make_workload("c5", 1)
+        _, flat = self.model_of(w, "c5")
+        full = make_workload("c5full", 1)
+        idx = np.linspace(0, full['xp'].size - 1, npoints).astype(np.int64)
+        pts = [self.torch.from_numpy(np.ascontiguousarray(full[k][idx])).to(self.tdev) for k in ('xp', 'yp', 'zp')]
+        with partition.PrismShards(flat, ['gz'], device=self.dev) as shards:
+            for _ in range(3):
+                shards.fields_device(*pts)
+            self.barrier()
+            k_ms = c_ms = 0.0
+            for _ in range(steps):
+                self._lib.check(self.lib.fb200_flush_l2(self.dev))
+                shards.fields_device(*pts)
+                k_ms += shards.timings["kernel_ms"]
+                c_ms += shards.timings["collective_ms"]
+            nbytes = shards.timings["collective_bytes"]
+            self.barrier()
+        k_max, c_max, t_max = self.reduce([k_ms / steps, c_ms / steps, (k_ms + c_ms) / steps], "MAX")
+        pairs = float(npoints) * flat.size
+        nw = self.world
+        return {"workload": "10^4 points x 10^6-prism relief, gz, prisms sharded over %d GPU(s) "
+                            "(per-cell kernels on each shard), partial fields all-reduced on the GPUs" % nw,
+                "value": pairs / (t_max * 1e-3), "unit": UNIT, "ms_per_step": t_max, "steps": steps, "warmup": 3,
+                "kernel_ms": k_max, "collective_ms": c_max, "collective_bytes": nbytes,
+                "collective_algbw_gbs": nbytes / 1e9 / (c_max * 1e-3) if c_max > 0 else None,
+                "collective_busbw_gbs": (nbytes / 1e9 / (c_max * 1e-3) * 2.0 * (nw - 1) / nw) if c_max > 0 else None,
+                "collective": "ncclAllReduce(sum, fp64) through torch.distributed on the GPU tensors; "
+                              "fixed reduction tree: reruns reproduce",
+                "scaling": "strong"}
+
     def close(self):
         for model, _ in self.models.values():
             model.close()
         if self.dist is not None:
             self.dist.barrier()
             self.dist.destroy_process_group()
+        elif getattr(self, "_own_group", None) is not None:
+            self._own_group.destroy_process_group()
 
 
 def run_gpu(args):
@@ -652,12 +702,13 @@ def run_gpu(args):
     main = B.measure(args.workload, args.steps, args.warmup, weak=not args.workload.endswith(("full", "slab")),
                      e2e_steps=0 if args.no_e2e else max(1, min(args.steps, 3)), clocks=True)
     extra = {}
-    strong = None
+    strong = pshard = None
     if args.workload == "c2" and not args.no_configs:
         for name in ("c3", "c4", "c5", "c5t"):
             extra[name] = B.measure(name, 3, 3, weak=True, e2e_steps=0,
                                     model_key="c5" if name.startswith("c5") else name)
         strong = B.measure("c5tslab", 2, 3, weak=False, model_key="c5")
+        pshard = B.prism_shard()
 
     line = None
     if rank == 0:
@@ -713,6 +764,8 @@ def run_gpu(args):
                          "the full 1e6 x 1e6 problem is 16 slabs (seconds = 16 x ms_per_step / 1000)")
             s["north_star_seconds_at_this_n"] = 16.0 * strong['ms_per_step'] / 1e3
             line["strong"] = s
+        if pshard is not None:
+            line["prism_shard"] = pshard
         if parity:
             line["parity"] = parity
         print(json.dumps(line), flush=True)

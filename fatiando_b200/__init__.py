@@ -25,5 +25,6 @@ from . import constants, gridder, mesher, utils          # noqa: F401
 from . import flatten, prism, _prism, partition          # noqa: F401
 from . import harvester, sphere, polyprism, imaging      # noqa: F401
 from .mesher import Prism, PrismMesh, PrismRelief, Sphere, PolygonalPrism    # noqa: F401
+from ._lib import pinned_empty                            # noqa: F401
 
 __version__ = "0.1.0"

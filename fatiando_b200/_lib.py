@@ -64,6 +64,9 @@ _SIGNATURES = {
     "fb200_prism_bz": ([_dp, _dp, _dp, _i64] + [_d] * 9 + [_dp], ctypes.c_int),
     "fb200_last_kernel_ms": ([ctypes.c_void_p, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int)],
                              ctypes.c_int),
+    "fb200_last_fallback_points": ([ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)], ctypes.c_int),
+    "fb200_host_alloc": ([ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
+    "fb200_host_free": ([ctypes.c_void_p], ctypes.c_int),
     "fb200_fp64_peak": ([ctypes.c_int, _d, ctypes.POINTER(_d), ctypes.POINTER(_d)], ctypes.c_int),
     "fb200_flush_l2": ([ctypes.c_int], ctypes.c_int),
     "fb200_debug_math": ([ctypes.c_int, ctypes.c_int, _dp, _dp, _i64, _dp], ctypes.c_int),
@@ -136,3 +139,56 @@ def require_device():
     n = ctypes.c_int(0)
     check(lib().fb200_device_count(ctypes.byref(n)))
     return n.value
+
+
+# Page-locked buffers are expensive to create (the OS pins every page) and cheap to reuse: a
+# released buffer goes back to this pool and serves the next request of the same size.
+_PINNED_POOL = {}
+_PINNED_POOL_BYTES = [0]
+PINNED_POOL_LIMIT = 32 << 30          # bytes kept for reuse; beyond that buffers are freed
+
+
+def _pinned_release(nbytes, address):
+    if _lib is None:
+        return
+    if _PINNED_POOL_BYTES[0] + nbytes <= PINNED_POOL_LIMIT:
+        _PINNED_POOL.setdefault(nbytes, []).append(address)
+        _PINNED_POOL_BYTES[0] += nbytes
+    else:
+        _lib.fb200_host_free(ctypes.c_void_p(address))
+
+
+def pinned_pool_clear():
+    """Free every pooled page-locked buffer."""
+    for nbytes, addresses in list(_PINNED_POOL.items()):
+        for address in addresses:
+            _lib.fb200_host_free(ctypes.c_void_p(address))
+    _PINNED_POOL.clear()
+    _PINNED_POOL_BYTES[0] = 0
+
+
+def pinned_empty(shape, dtype="float64"):
+    """
+    An uninitialised numpy array in page-locked host memory (fb200_host_alloc): a destination
+    that ``Model.jacobian(..., out=...)`` fills at PCIe DMA speed (pageable memory goes through
+    the driver's bounce buffers, and a fresh pageable array pays a page fault per 4 KB on top).
+    When the array and every view of it are gone the buffer returns to a pool and serves the
+    next request of the same size.
+    """
+    import weakref
+    import numpy
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    dt = numpy.dtype(dtype)
+    nbytes = max(1, int(numpy.prod(shape, dtype=numpy.int64)) * dt.itemsize)
+    pooled = _PINNED_POOL.get(nbytes)
+    if pooled:
+        address = pooled.pop()
+        _PINNED_POOL_BYTES[0] -= nbytes
+    else:
+        ptr = ctypes.c_void_p()
+        check(lib().fb200_host_alloc(nbytes, ctypes.byref(ptr)))
+        address = ptr.value
+    buf = (ctypes.c_char * nbytes).from_address(address)
+    arr = numpy.frombuffer(buf, dtype=dt, count=nbytes // dt.itemsize).reshape(shape)
+    weakref.finalize(buf, _pinned_release, nbytes, address)
+    return arr

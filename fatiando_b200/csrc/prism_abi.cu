@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -95,6 +96,11 @@ struct fb200_model {
     double *d_face[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x1 x2 y1 y2 zf zo w
     double *d_snode[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // xn shx yn shy zn zn w
     int *d_flag = nullptr;
+    int last_fallback_points = 0;                      // points the last call re-evaluated per cell
+    cudaStream_t copy_stream = nullptr;                // D2H of Jacobian row blocks (overlaps the kernels)
+    cudaEvent_t ev_built[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    double *d_iwork = nullptr; size_t iwork_cap = 0;   // per-point flags + index list (ints)
+    double *d_sub = nullptr;   size_t sub_cap = 0;     // gathered points and their results (per-point fallback)
     double *d_adj = nullptr; size_t adj_cap = 0;       // node-sharing adjoint: point rows, node list, V
     // cell walls whose coordinate the reference computes differently from the two sides
     // (x2 of one cell != x1 of the next, one ulp apart): see fb200_model_set_hazard_planes
@@ -194,8 +200,10 @@ __global__ void canonical_zero_kernel(double *p, int64_t n)
     if (i < n) p[i] = p[i] + 0.0;
 }
 
-// *flag = 1 when some coordinate c[l] lies within a few ulp of one of the (sorted) planes
-__global__ void near_plane_kernel(const double *c, int64_t n, const double *planes, int64_t np, int *flag)
+// *flag = 1 (and pflag[l] = 1, when given) for a coordinate c[l] within a few ulp of one of the
+// (sorted) planes
+__global__ void near_plane_kernel(const double *c, int64_t n, const double *planes, int64_t np, int *flag,
+                                  int *pflag = nullptr)
 {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n) return;
@@ -211,7 +219,53 @@ __global__ void near_plane_kernel(const double *c, int64_t n, const double *plan
         const double p = planes[k];
         near = near || fabs(v - p) <= 0x1p-49 * fmax(fabs(v), fabs(p));     // 8 ulp
     }
-    if (near) *flag = 1;
+    if (near) {
+        *flag = 1;
+        if (pflag) pflag[l] = 1;
+    }
+}
+
+// ---- per-point fallback of the merged forms ---------------------------------------
+// idx[0 .. *count) = the flagged points, ascending (one block-wide ordered pass per 1024 points
+// would be overkill: the list is short, an atomic append followed by a sort on the host side is
+// not needed either -- every flagged point is evaluated on its own, the order is irrelevant)
+__global__ void compact_flags_kernel(const int *pflag, int64_t n, int *idx, int *count)
+{
+    const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n && pflag[l]) idx[atomicAdd(count, 1)] = (int)l;
+}
+
+__global__ void gather_points_kernel(const double *xp, const double *yp, const double *zp, const int *idx,
+                                     int64_t k, int64_t k_pad, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const int l = idx[i];
+    out[i] = xp[l]; out[k_pad + i] = yp[l]; out[2 * k_pad + i] = zp[l];
+}
+
+// out[c*ld_out + idx[i]] = sub[c*ld_sub + i]
+__global__ void scatter_fields_kernel(const double *sub, int64_t ld_sub, const int *idx, int64_t k,
+                                      double *out, int64_t ld_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    out[(int64_t)blockIdx.y * ld_out + idx[i]] = sub[(int64_t)blockIdx.y * ld_sub + i];
+}
+
+// rows of a Jacobian: out(idx[i] - row0, q) = sub(i, q), either layout; rows outside
+// [row0, row0 + nrows) are skipped (host-streamed row blocks)
+__global__ void scatter_rows_kernel(const double *sub, int64_t ld_sub, int transposed_sub, const int *idx,
+                                    int64_t k, int64_t m, int64_t row0, int64_t nrows, double *out,
+                                    int64_t ld_out, int transposed)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (q >= m || i >= k) return;
+    const int64_t l = (int64_t)idx[i] - row0;
+    if (l < 0 || l >= nrows) return;
+    const double v = transposed_sub ? sub[q * ld_sub + i] : sub[i * ld_sub + q];
+    if (transposed) out[q * ld_out + l] = v; else out[l * ld_out + q] = v;
 }
 
 // ---- node-sharing adjoint helpers (fb200_adjoint) ------------------------------
@@ -372,8 +426,18 @@ extern "C" int fb200_model_destroy(fb200_model *model)
     for (int r = 0; r < 7; ++r)
         if (model->d_snode[r] && r != 5) cudaFreeAsync(model->d_snode[r], st);   // row 5 aliases row 4
     if (model->d_flag) cudaFreeAsync(model->d_flag, st);
+    if (model->d_iwork) cudaFreeAsync(model->d_iwork, st);
+    if (model->d_sub) cudaFreeAsync(model->d_sub, st);
     if (model->d_adj) cudaFreeAsync(model->d_adj, st);
     for (double *p : model->d_hazard) if (p) cudaFreeAsync(p, st);
+    if (model->copy_stream) {
+        cudaStreamSynchronize(model->copy_stream);
+        cudaStreamDestroy(model->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (model->ev_built[i]) cudaEventDestroy(model->ev_built[i]);
+            if (model->ev_copy[i]) cudaEventDestroy(model->ev_copy[i]);
+        }
+    }
     StreamSet set;
     set.stream = model->stream; set.ev0 = model->ev0; set.ev1 = model->ev1;
     release_streams(model->device, set);
@@ -609,6 +673,29 @@ extern "C" int fb200_model_set_hazard_planes(fb200_model *mod, int64_t nx, const
 extern "C" int64_t fb200_model_size(const fb200_model *model) { return model ? model->m : -1; }
 extern "C" int fb200_model_device(const fb200_model *model) { return model ? model->device : -1; }
 
+// Page-locked host memory for destinations that are filled again and again (a host-resident
+// Jacobian crosses PCIe at DMA speed into it; pageable memory goes through bounce buffers).
+extern "C" int fb200_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr) return fail(FB200_EINVAL, "ptr is NULL");
+    *ptr = nullptr;
+    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return FB200_OK;
+}
+
+extern "C" int fb200_host_free(void *ptr)
+{
+    if (ptr) CK(cudaFreeHost(ptr));
+    return FB200_OK;
+}
+
+extern "C" int fb200_last_fallback_points(const fb200_model *model, int *points)
+{
+    if (!model || !points) return fail(FB200_EINVAL, "NULL argument");
+    *points = model->last_fallback_points;
+    return FB200_OK;
+}
+
 extern "C" int fb200_last_kernel_ms(const fb200_model *model, double *ms, int *launches)
 {
     if (!model) return fail(FB200_EINVAL, "model is NULL");
@@ -735,12 +822,12 @@ static int run_set_mesh(fb200_model *mod, uint32_t set, uint32_t request, bool a
 // partial sums side by side, one fixed-order reduction adds them.
 static int run_set_surface(fb200_model *mod, uint32_t set, uint32_t request, bool allow_split,
                            const double *d_xp, const double *d_yp, const double *d_zp, int64_t n,
-                           const double *scale, double *d_out, int64_t ld_out)
+                           const double *scale, double *d_out, int64_t ld_out, int *d_pflag)
 {
     ForwardArgs a;
     std::memset(&a, 0, sizeof(a));
     a.xp = d_xp; a.yp = d_yp; a.zp = d_zp; a.n = n;
-    a.flag = mod->d_flag;
+    a.flag = d_pflag;
     const int nc = popc(set);
     int c = 0;
     for (int f = 0; f < F_COUNT; ++f) {
@@ -891,6 +978,7 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
     if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
     mod->last_launches = 0;
     mod->last_ms = 0.0;
+    mod->last_fallback_points = 0;
 
     const double *d_xp = xp, *d_yp = yp, *d_zp = zp, *d_init = init;
     double *d_out = out;
@@ -930,43 +1018,41 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
                        !dens_override;
         // Where the reference's two cells disagree on a shared wall by an ulp, a point IN that
         // wall gets direction-dependent terms (atan2 of +-0 denominators) that do not cancel in
-        // the reference; the merged forms cannot reproduce that, the per-cell kernels do.
-        if ((nodes_ok || surface) && (mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2])) {
+        // the reference; the merged forms cannot reproduce that, the per-cell kernels do.  Such
+        // points -- and those where a merged reference-plane node meets the thickness-dependent
+        // shift of gxz / gyz (prism_face.cuh: EvalNode) -- are flagged one by one, evaluated
+        // by the per-cell kernels afterwards and scattered over the merged forms' output.
+        const bool hazards = mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2];
+        int *d_pflag = nullptr, *d_idx = nullptr;
+        const int64_t n_pad = (n + 63) / 64 * 64;
+        if ((nodes_ok && hazards) || surface) {
+            int rc = grow(&mod->d_iwork, &mod->iwork_cap, (size_t)n_pad + 8, mod->stream);   // 2 n_pad ints
+            if (rc != FB200_OK) return rc;
+            d_pflag = reinterpret_cast<int *>(mod->d_iwork);
+            d_idx = d_pflag + n_pad;
+            CK(cudaMemsetAsync(d_pflag, 0, (size_t)n * sizeof(int), mod->stream));
             CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
-            const double *coord[3] = {d_xp, d_yp, d_zp};
-            for (int ax = 0; ax < 3; ++ax) {
-                if (!mod->n_hazard[ax]) continue;
-                near_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(
-                    coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag);
-                CK(cudaGetLastError());
-            }
-            int raised = 0;
-            CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
-            CK(cudaStreamSynchronize(mod->stream));
-            if (raised) nodes_ok = surface = false;
-        }
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            if (surface) CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
-            if (gmask) {
-                const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
-                for (uint32_t set : sibling ? cover(gmask, kSphereGravitySets) : cover(gmask, kGravitySets)) {
-                    int rc = surface
-                        ? run_set_surface(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, scale, d_out, ld)
-                        : use_nodes
-                        ? run_set_mesh(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, fvec, scale, d_out, ld)
-                        : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
-                                  dens_override, fvec, scale, d_init, d_out, ld);
-                    if (rc != FB200_OK) return rc;
+            if (hazards) {
+                const double *coord[3] = {d_xp, d_yp, d_zp};
+                for (int ax = 0; ax < 3; ++ax) {
+                    if (!mod->n_hazard[ax]) continue;
+                    near_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(
+                        coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag, d_pflag);
+                    CK(cudaGetLastError());
                 }
             }
-            if (!surface) break;
-            // a merged reference-plane node met the thickness-dependent shift of gxz / gyz
-            // (prism_face.cuh: EvalNode): evaluate this call cell by cell instead
-            int raised = 0;
-            CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
-            CK(cudaStreamSynchronize(mod->stream));
-            if (!raised) break;
-            surface = false;
+        }
+        if (gmask) {
+            const bool use_nodes = nodes_ok && mod->d_wdens && !dens_override;
+            for (uint32_t set : sibling ? cover(gmask, kSphereGravitySets) : cover(gmask, kGravitySets)) {
+                int rc = surface
+                    ? run_set_surface(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, scale, d_out, ld, d_pflag)
+                    : use_nodes
+                    ? run_set_mesh(mod, set, field_mask, split, d_xp, d_yp, d_zp, n, fvec, scale, d_out, ld)
+                    : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
+                              dens_override, fvec, scale, d_init, d_out, ld);
+                if (rc != FB200_OK) return rc;
+            }
         }
         if (mmask) {
             const bool use_nodes = nodes_ok && mod->d_wmag[0] && !pmag_override;
@@ -976,6 +1062,54 @@ static int forward_impl(fb200_model *mod, const double *xp, const double *yp, co
                     : run_set(mod, set, field_mask, exact, split, d_xp, d_yp, d_zp, n,
                               pmag_override, fvec, scale, d_init, d_out, ld);
                 if (rc != FB200_OK) return rc;
+            }
+        }
+        if (d_pflag) {
+            // the flagged points, cell by cell: exactly what a per-cell call on those points
+            // alone returns (the prism split, hence the last bits, depends on the point count)
+            int *d_count = mod->d_flag;
+            CK(cudaMemsetAsync(d_count, 0, sizeof(int), mod->stream));
+            compact_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(d_pflag, n, d_idx, d_count);
+            CK(cudaGetLastError());
+            int k = 0;
+            CK(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+            CK(cudaStreamSynchronize(mod->stream));
+            mod->last_fallback_points = k;
+            if (k > 0) {
+                const int64_t k_pad = ((int64_t)k + 31) / 32 * 32;
+                int rc = grow(&mod->d_sub, &mod->sub_cap, (size_t)k_pad * (3 + nreq), mod->stream);
+                if (rc != FB200_OK) return rc;
+                double *sx = mod->d_sub, *sout = mod->d_sub + 3 * k_pad;
+                gather_points_kernel<<<(unsigned)((k + 255) / 256), 256, 0, mod->stream>>>(
+                    d_xp, d_yp, d_zp, d_idx, k, k_pad, sx);
+                CK(cudaGetLastError());
+                const bool merged_g = surface || (nodes_ok && mod->d_wdens && !dens_override);
+                const bool merged_m = nodes_ok && mod->d_wmag[0] && !pmag_override;
+                uint32_t redo = 0;
+                if (gmask && merged_g) {
+                    redo |= gmask;
+                    for (uint32_t set : cover(gmask, kGravitySets)) {
+                        rc = run_set(mod, set, field_mask, false, split, sx, sx + k_pad, sx + 2 * k_pad, k,
+                                     dens_override, fvec, scale, nullptr, sout, k_pad);
+                        if (rc != FB200_OK) return rc;
+                    }
+                }
+                if (mmask && merged_m) {
+                    redo |= mmask;
+                    for (uint32_t set : cover(mmask, kMagneticSets)) {
+                        rc = run_set(mod, set, field_mask, false, split, sx, sx + k_pad, sx + 2 * k_pad, k,
+                                     pmag_override, fvec, scale, nullptr, sout, k_pad);
+                        if (rc != FB200_OK) return rc;
+                    }
+                }
+                for (int f = 0; f < F_COUNT; ++f) {
+                    if (!(redo & bit(f))) continue;
+                    const int row = popc(field_mask & (bit(f) - 1));
+                    scatter_fields_kernel<<<dim3((unsigned)((k + 255) / 256), 1), 256, 0, mod->stream>>>(
+                        sout + (int64_t)row * k_pad, k_pad, d_idx, k, d_out + (int64_t)row * ld, ld);
+                    CK(cudaGetLastError());
+                }
+                mod->last_launches += 2;
             }
         }
         CK(cudaEventRecord(mod->ev1, mod->stream));
@@ -1006,6 +1140,18 @@ extern "C" int fb200_forward(fb200_model *model, const double *xp, const double 
 // ---------------------------------------------------------------------------
 // Jacobian
 // ---------------------------------------------------------------------------
+// second stream + events of the host-destination pipeline, created on first use
+static int ensure_copy_stream(fb200_model *mod)
+{
+    if (mod->copy_stream) return FB200_OK;
+    CK(cudaStreamCreateWithFlags(&mod->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&mod->ev_built[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&mod->ev_copy[i], cudaEventDisableTiming));
+    }
+    return FB200_OK;
+}
+
 extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *yp,
                               const double *zp, int64_t n, int field, const double *unit_prop,
                               const double *fvec, double scale, double *out, int64_t ld,
@@ -1075,31 +1221,71 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
         return exact ? launch_jacobian_exact(field, transposed, args, mod->stream)
                      : launch_jacobian_fast(field, transposed, args, mod->stream);
     };
-    auto hazard_hit = [&](const double *dx, const double *dy, const double *dz, int64_t cnt, bool *hit) -> int {
-        *hit = false;
+    // Points lying in a hazard wall (see forward_impl) get their rows from the per-cell
+    // kernels: flagged one by one, the whole call runs by node sharing, then those rows are
+    // recomputed cell by cell and written over.
+    int *d_idx = nullptr;
+    int n_flagged = 0;
+    auto flag_hazards = [&](const double *dx, const double *dy, const double *dz) -> int {
         if (!(mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2])) return FB200_OK;
+        const int64_t n_pad = (n + 63) / 64 * 64;
+        int rc = grow(&mod->d_iwork, &mod->iwork_cap, (size_t)n_pad + 8, mod->stream);
+        if (rc != FB200_OK) return rc;
+        int *d_pflag = reinterpret_cast<int *>(mod->d_iwork);
+        d_idx = d_pflag + n_pad;
+        CK(cudaMemsetAsync(d_pflag, 0, (size_t)n * sizeof(int), mod->stream));
         CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
         const double *coord[3] = {dx, dy, dz};
         for (int ax = 0; ax < 3; ++ax) {
             if (!mod->n_hazard[ax]) continue;
-            near_plane_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, mod->stream>>>(
-                coord[ax], cnt, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag);
+            near_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(
+                coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag, d_pflag);
             CK(cudaGetLastError());
         }
-        int raised = 0;
-        CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+        CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+        compact_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(d_pflag, n, d_idx, mod->d_flag);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&n_flagged, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
         CK(cudaStreamSynchronize(mod->stream));
-        *hit = raised != 0;
+        mod->last_fallback_points = n_flagged;
         return FB200_OK;
     };
+    // per-cell rows of the flagged points, in blocks of <= 64 MiB, written over rows
+    // [row0, row0 + nrows) of a device matrix `dst` (leading dimension ldd)
+    auto redo_flagged = [&](const double *dx, const double *dy, const double *dz, double *dst, int64_t ldd,
+                            int64_t row0, int64_t nrows) -> int {
+        if (n_flagged == 0) return FB200_OK;
+        const int64_t per = std::max<int64_t>(1, std::min<int64_t>(n_flagged, ((int64_t)(64ll << 20) / 8) / std::max<int64_t>(m, 1)));
+        const int64_t per_pad = (per + 31) / 32 * 32;
+        int rc = grow(&mod->d_sub, &mod->sub_cap, (size_t)per_pad * 3 + (size_t)per_pad * m, mod->stream);
+        if (rc != FB200_OK) return rc;
+        double *sx = mod->d_sub, *sj = mod->d_sub + 3 * per_pad;
+        const bool keep = by_nodes;
+        by_nodes = false;
+        for (int64_t i0 = 0; i0 < n_flagged; i0 += per) {
+            const int64_t k = std::min<int64_t>(per, n_flagged - i0);
+            gather_points_kernel<<<(unsigned)((k + 255) / 256), 256, 0, mod->stream>>>(
+                dx, dy, dz, d_idx + i0, k, per_pad, sx);
+            CK(cudaGetLastError());
+            JacobianArgs s2 = a;
+            s2.xp = sx; s2.yp = sx + per_pad; s2.zp = sx + 2 * per_pad; s2.n = k;
+            s2.out = sj; s2.ld = transposed ? k : m;
+            CK(launch(s2));
+            scatter_rows_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)k), 256, 0, mod->stream>>>(
+                sj, s2.ld, transposed ? 1 : 0, d_idx + i0, k, m, row0, nrows, dst, ldd, transposed ? 1 : 0);
+            CK(cudaGetLastError());
+            mod->last_launches += 2;
+        }
+        by_nodes = keep;
+        return FB200_OK;
+    };
+    mod->last_fallback_points = 0;
     // points per launch: grid.y limit, and (host output) a bounded staging block
     const int64_t max_rows_grid = (int64_t)65535 * JAC_TILE;
     if (on_device) {
         if (by_nodes) {
-            bool hit = false;
-            int rc = hazard_hit(xp, yp, zp, n, &hit);
+            int rc = flag_hazards(xp, yp, zp);
             if (rc != FB200_OK) return rc;
-            if (hit) by_nodes = false;
         }
         CK(cudaEventRecord(mod->ev0, mod->stream));
         for (int64_t r0 = 0; r0 < n; r0 += max_rows_grid) {
@@ -1110,6 +1296,10 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
             CK(launch(a));
             mod->last_launches += 1;
         }
+        if (by_nodes) {
+            int rc = redo_flagged(xp, yp, zp, out, ld, 0, n);
+            if (rc != FB200_OK) return rc;
+        }
         CK(cudaEventRecord(mod->ev1, mod->stream));
         CK(cudaStreamSynchronize(mod->stream));
         float ms = 0.f;
@@ -1117,7 +1307,8 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
         mod->last_ms = ms;
         return FB200_OK;
     }
-    // host output: stream the matrix back in row blocks of <= 256 MiB
+    // host output: the matrix is built in row blocks on the device and streamed back through
+    // two staging blocks -- the kernel of block k+1 runs while block k crosses PCIe
     const int64_t np = (n + 31) / 32 * 32;
     int rc = grow(&mod->d_pts, &mod->pts_cap, (size_t)np * 3, mod->stream);
     if (rc != FB200_OK) return rc;
@@ -1125,38 +1316,65 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     CK(cudaMemcpyAsync(mod->d_pts + np, yp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     CK(cudaMemcpyAsync(mod->d_pts + 2 * np, zp, (size_t)n * 8, cudaMemcpyHostToDevice, mod->stream));
     if (by_nodes) {
-        bool hit = false;
-        rc = hazard_hit(mod->d_pts, mod->d_pts + np, mod->d_pts + 2 * np, n, &hit);
+        rc = flag_hazards(mod->d_pts, mod->d_pts + np, mod->d_pts + 2 * np);
         if (rc != FB200_OK) return rc;
-        if (hit) by_nodes = false;
     }
-    int64_t rows = std::max<int64_t>(JAC_TILE, ((int64_t)(256ll << 20) / 8 / m) / JAC_TILE * JAC_TILE);
+    // row blocks of <= 128 MiB, two of them in flight
+    int64_t rows = std::max<int64_t>(JAC_TILE, ((int64_t)(128ll << 20) / 8 / m) / JAC_TILE * JAC_TILE);
     rows = std::min(rows, std::min(max_rows_grid, (n + JAC_TILE - 1) / JAC_TILE * JAC_TILE));
-    rc = grow(&mod->d_out, &mod->out_cap, (size_t)rows * m, mod->stream);
+    rc = grow(&mod->d_out, &mod->out_cap, (size_t)2 * rows * m, mod->stream);
     if (rc != FB200_OK) return rc;
-    double total_ms = 0.0;
-    for (int64_t r0 = 0; r0 < n; r0 += rows) {
+    rc = ensure_copy_stream(mod);
+    if (rc != FB200_OK) return rc;
+    // pin the destination for the duration of the call when it is large: pageable memory
+    // crosses PCIe through the driver's bounce buffers at a few GB/s
+    bool pinned_here = false;
+    const size_t out_bytes = (size_t)(transposed ? m : n) * (size_t)ld * 8;
+    cudaPointerAttributes attr;
+    const bool already = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    static const bool no_register = std::getenv("FB200_NO_HOST_REGISTER") != nullptr;
+    if (!already && !no_register && out_bytes >= ((size_t)32 << 20))
+        pinned_here = cudaHostRegister(out, out_bytes, cudaHostRegisterDefault) == cudaSuccess;
+    if (!pinned_here) (void)cudaGetLastError();
+    CK(cudaEventRecord(mod->ev0, mod->stream));
+    int64_t blk = 0;
+    int status = FB200_OK;
+    for (int64_t r0 = 0; r0 < n && status == FB200_OK; r0 += rows, ++blk) {
         const int64_t rb = std::min(rows, n - r0);
+        double *stage = mod->d_out + (size_t)(blk & 1) * rows * m;
+        // the staging block is free once its previous copy (two blocks ago) has finished
+        if (blk >= 2 && cudaStreamWaitEvent(mod->stream, mod->ev_copy[blk & 1], 0) != cudaSuccess) { status = FB200_ECUDA; break; }
         a.xp = mod->d_pts + r0; a.yp = mod->d_pts + np + r0; a.zp = mod->d_pts + 2 * np + r0;
         a.n = rb;
-        a.out = mod->d_out;
+        a.out = stage;
         a.ld = transposed ? rb : m;
-        CK(cudaEventRecord(mod->ev0, mod->stream));
-        CK(launch(a));
-        CK(cudaEventRecord(mod->ev1, mod->stream));
+        if (launch(a) != cudaSuccess) { status = FB200_ECUDA; break; }
         mod->last_launches += 1;
+        if (by_nodes && n_flagged) {
+            status = redo_flagged(mod->d_pts, mod->d_pts + np, mod->d_pts + 2 * np, stage, a.ld, r0, rb);
+            if (status != FB200_OK) break;
+        }
+        if (cudaEventRecord(mod->ev_built[blk & 1], mod->stream) != cudaSuccess) { status = FB200_ECUDA; break; }
+        if (cudaStreamWaitEvent(mod->copy_stream, mod->ev_built[blk & 1], 0) != cudaSuccess) { status = FB200_ECUDA; break; }
+        cudaError_t ce;
         if (!transposed)
-            CK(cudaMemcpy2DAsync(out + r0 * ld, (size_t)ld * 8, mod->d_out, (size_t)m * 8,
-                                 (size_t)m * 8, (size_t)rb, cudaMemcpyDeviceToHost, mod->stream));
+            ce = cudaMemcpy2DAsync(out + r0 * ld, (size_t)ld * 8, stage, (size_t)m * 8,
+                                   (size_t)m * 8, (size_t)rb, cudaMemcpyDeviceToHost, mod->copy_stream);
         else
-            CK(cudaMemcpy2DAsync(out + r0, (size_t)ld * 8, mod->d_out, (size_t)rb * 8,
-                                 (size_t)rb * 8, (size_t)m, cudaMemcpyDeviceToHost, mod->stream));
-        CK(cudaStreamSynchronize(mod->stream));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
-        total_ms += ms;
+            ce = cudaMemcpy2DAsync(out + r0, (size_t)ld * 8, stage, (size_t)rb * 8,
+                                   (size_t)rb * 8, (size_t)m, cudaMemcpyDeviceToHost, mod->copy_stream);
+        if (ce != cudaSuccess || cudaEventRecord(mod->ev_copy[blk & 1], mod->copy_stream) != cudaSuccess) { status = FB200_ECUDA; break; }
     }
-    mod->last_ms = total_ms;
+    cudaError_t e1 = cudaEventRecord(mod->ev1, mod->stream);
+    cudaError_t e2 = cudaStreamSynchronize(mod->copy_stream);
+    cudaError_t e3 = cudaStreamSynchronize(mod->stream);
+    if (pinned_here) cudaHostUnregister(out);
+    if (status != FB200_OK) return fail(status, "Jacobian row-block pipeline failed");
+    CK(e1); CK(e2); CK(e3);
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+    mod->last_ms = ms;       // device time of the kernels (the copies overlap them on the copy stream)
     return FB200_OK;
 }
 

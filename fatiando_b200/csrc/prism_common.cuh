@@ -78,7 +78,7 @@ struct ForwardArgs {
     const double *init;      // optional starting value of the running sum (ncomp == 1)
     double scale[F_COUNT];   // per component of this launch, ascending field order
     int out_row[F_COUNT];    // destination row of each component
-    int *flag;               // raised by evaluators that meet a case they cannot settle (EvalNode)
+    int *flag;               // flag[l] raised for a point where an evaluator meets a case it cannot settle (EvalNode)
 };
 
 }  // namespace fb200

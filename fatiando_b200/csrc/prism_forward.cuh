@@ -151,7 +151,7 @@ forward_kernel(const ForwardArgs a)
             if constexpr (Eval::NEEDS_FLAG)
                 Eval::template pair_flag<MASK>(acc, xp, yp, zp, sp[s][0][q], sp[s][1][q], sp[s][2][q],
                                                sp[s][3][q], sp[s][4][q], sp[s][5][q], p0, p1, p2, f,
-                                               a.flag);
+                                               a.flag + l);
             else
                 Eval::template pair<MASK>(acc, xp, yp, zp, sp[s][0][q], sp[s][1][q], sp[s][2][q],
                                           sp[s][3][q], sp[s][4][q], sp[s][5][q], p0, p1, p2, f);

@@ -110,9 +110,109 @@ def fields_observation_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, 
                     np.ascontiguousarray(zp[sl]), names, dens=dens, pmag=pmag, fvec=fvec, **kw)
     if not gather:
         return mine, sl
-    parts = [None] * world
-    dist.all_gather_object(parts, {k: np.asarray(v) for k, v in mine.items()})
-    return {nm: np.hstack([p[nm] for p in parts]) for nm in mine}
+    if dist.get_backend() != 'nccl':
+        # gloo (CPU tests): small arrays, pickled
+        parts = [None] * world
+        dist.all_gather_object(parts, {k: np.asarray(v) for k, v in mine.items()})
+        return {nm: np.hstack([p[nm] for p in parts]) for nm in mine}
+    # NCCL: one all-gather of a float64 tensor padded to the largest chunk (the last chunk takes
+    # the remainder), no pickling through the GPU
+    import torch
+    order = list(mine)
+    bounds = chunk_bounds(xp.size, world)
+    widest = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
+    dev = torch.device('cuda', default_device(rank) if device is None else device)
+    local = torch.zeros((len(order), widest), dtype=torch.float64, device=dev)
+    stacked = np.stack([np.asarray(mine[nm], dtype=np.float64) for nm in order])
+    local[:, :stacked.shape[1]] = torch.from_numpy(stacked).to(dev)
+    everything = torch.empty((world, len(order), widest), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(everything, local)
+    host = everything.cpu().numpy()
+    return {nm: np.hstack([host[r, i, :bounds[r + 1] - bounds[r]] for r in range(world)])
+            for i, nm in enumerate(order)}
+
+
+class PrismShards(object):
+    """
+    Prism-sharded evaluation, device-resident: this rank's contiguous slice of the prisms is
+    uploaded ONCE; :meth:`fields` evaluates the partial fields of all points straight into a
+    GPU tensor (``FB200_DEVICE_POINTERS``), adds the ranks' partials with ONE all-reduce on the
+    GPUs (NCCL over NVLink) and applies the unit factors to the sum.  Nothing crosses PCIe
+    between the kernel and the collective.  Ranks are added by the collective's fixed tree:
+    reruns reproduce, and the result equals a single-GPU run to within the parity floor (the
+    summation order differs).
+
+    ``timings`` of the last call: kernel milliseconds (library stream, CUDA events), collective
+    milliseconds (torch stream, CUDA events) and the bytes each rank contributed.
+    """
+
+    def __init__(self, prisms, names, dens=None, pmag=None, fvec=None, device=None):
+        import torch
+        dist = _dist()
+        self.dist, self.torch = dist, torch
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        flat, prop = _flatten_for(prisms, names, dens, pmag, fvec)
+        sl = local_slice(flat.size, self.rank, self.world)
+        part = FlatModel([b[sl] for b in flat.bounds],
+                         None if flat.density is None else flat.density[sl],
+                         None if flat.magnetization is None else flat.magnetization[sl],
+                         flat.index[sl], flat.total)
+        self.device = default_device(self.rank) if device is None else device
+        self.names = list(names)
+        self.prop, self.total_prisms, self.slice = prop, flat.size, sl
+        self.fvec = None if fvec is None else np.ascontiguousarray(fvec, dtype=np.float64)
+        self.model = _prism_api.Model(part, prop, fvec=fvec, device=self.device, node_sharing=False)
+        self.timings = {}
+
+    def close(self):
+        self.model.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def fields_device(self, d_xp, d_yp, d_zp):
+        """``[ncomp, n]`` float64 CUDA tensor (rows in ascending field order, see ``order``) for
+        float64 CUDA tensors of point coordinates on this rank's device."""
+        from . import _lib
+        torch, dist = self.torch, self.dist
+        n = d_xp.numel()
+        ids = sorted(set(_lib.FIELD_ID[nm] for nm in self.names))
+        self.order = [_lib.FIELDS[i] for i in ids]
+        mask = 0
+        for i in ids:
+            mask |= 1 << i
+        out = torch.empty((len(ids), n), dtype=torch.float64, device=d_xp.device)
+        ones = np.ones(len(ids))
+        if self.model.size:
+            _lib.check(_lib.lib().fb200_forward(
+                self.model._handle, d_xp.data_ptr(), d_yp.data_ptr(), d_zp.data_ptr(), n, mask, None, None,
+                _lib.dptr(self.fvec), _lib.dptr(ones), out.data_ptr(), n, _lib.DEVICE_POINTERS))
+            kernel_ms = self.model.last_kernel_ms()[0]
+        else:
+            out.zero_()
+            kernel_ms = 0.0
+        # fb200_forward returns after its stream has drained: the partials are complete
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        e1.record()
+        scale = torch.tensor([_prism_api.unit_scale(nm) for nm in self.order], dtype=torch.float64,
+                             device=out.device)
+        out *= scale[:, None]
+        torch.cuda.synchronize(out.device)
+        self.timings = {"kernel_ms": kernel_ms, "collective_ms": e0.elapsed_time(e1),
+                        "collective_bytes": out.numel() * 8}
+        return out
+
+    def fields(self, xp, yp, zp):
+        torch = self.torch
+        dev = torch.device('cuda', self.device)
+        pts = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev) for a in (xp, yp, zp)]
+        total = self.fields_device(*pts).cpu().numpy()
+        return {nm: total[i] for i, nm in enumerate(self.order)}
 
 
 def fields_prism_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, fvec=None,
@@ -120,10 +220,17 @@ def fields_prism_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, fvec=N
     """
     Evaluate ``names`` with the PRISMS split over the ranks; the partial fields
     are summed with one all-reduce.  Unit factors are applied after the sum.
+
+    On the GPUs (NCCL backend, no ``evaluate`` hook, no overrides) this is
+    :class:`PrismShards`: partials stay in HBM, one NCCL all-reduce, nothing staged through
+    the host.  The host path below serves the ``gloo`` tests and overrides.
     """
     import torch
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
+    if evaluate is None and dist.get_backend() == 'nccl' and dens is None and pmag is None and not kw:
+        with PrismShards(prisms, names, fvec=fvec, device=device) as shards:
+            return shards.fields(xp, yp, zp)
     flat, prop = _flatten_for(prisms, names, dens, pmag, fvec)
     sl = local_slice(flat.size, rank, world)
     part = FlatModel([b[sl] for b in flat.bounds],
@@ -138,7 +245,7 @@ def fields_prism_sharded(xp, yp, zp, prisms, names, dens=None, pmag=None, fvec=N
     stacked = torch.from_numpy(np.stack([np.asarray(mine[nm]) for nm in order]))
     backend = dist.get_backend()
     if backend == 'nccl':
-        dev = torch.device('cuda', torch.cuda.current_device())
+        dev = torch.device('cuda', default_device(rank) if device is None else device)
         stacked = stacked.to(dev)
     dist.all_reduce(stacked, op=dist.ReduceOp.SUM)
     total = stacked.cpu().numpy()
@@ -200,7 +307,7 @@ def adjoint_point_sharded(xp, yp, zp, prisms, data, field='gz', pmag=None, fvec=
                     pmag=pmag, fvec=fvec, **kw)
     total = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.float64))
     if dist.get_backend() == 'nccl':
-        total = total.to(torch.device('cuda', torch.cuda.current_device()))
+        total = total.to(torch.device('cuda', default_device(rank) if device is None else device))
     dist.all_reduce(total, op=dist.ReduceOp.SUM)
     return total.cpu().numpy()
 

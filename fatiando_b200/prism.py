@@ -51,6 +51,9 @@ MAGNETIC_FIELDS = ('tf', 'bx', 'by', 'bz')
 # of the collapsed corner sums of the fast path would leave the double range).
 FAST_PATH_MAX_COORD = 1e15
 
+# Host-resident Jacobians of at least this many bytes are returned in page-locked memory.
+PINNED_OUTPUT_BYTES = 64 << 20
+
 # Regular meshes are evaluated node by node (each mesh node once, instead of once
 # per adjacent cell) when this is True; set to False to force the per-cell kernels.
 NODE_SHARING = True
@@ -233,7 +236,16 @@ class Model(object):
         n, m = xp.size, self.size
         shape = (m, n) if transposed else (n, m)
         if out is None:
-            out = numpy.zeros(shape, dtype=numpy.float64)
+            out = None
+            if n and m and n * m * 8 >= PINNED_OUTPUT_BYTES:
+                # large matrices land in page-locked memory (pooled, _lib.pinned_empty): the row
+                # blocks then cross PCIe at DMA speed while the next block is being computed
+                try:
+                    out = _lib.pinned_empty(shape)
+                except RuntimeError:
+                    out = None
+            if out is None:
+                out = numpy.zeros(shape, dtype=numpy.float64)
         if out.shape != shape or out.dtype != numpy.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
         if n and m:
@@ -291,6 +303,13 @@ class Model(object):
         _lib.check(_lib.lib().fb200_last_kernel_ms(self._handle, ctypes.byref(ms),
                                                    ctypes.byref(launches)))
         return ms.value, launches.value
+
+    def last_fallback_points(self):
+        """Points of the last evaluation that the per-cell kernels re-evaluated (hazard walls,
+        thickness-dependent shift of a merged relief node)."""
+        k = ctypes.c_int(0)
+        _lib.check(_lib.lib().fb200_last_fallback_points(self._handle, ctypes.byref(k)))
+        return k.value
 
 
 # --------------------------------------------------------------------------

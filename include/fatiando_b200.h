@@ -317,6 +317,17 @@ int64_t fb200_harvest_launches(const fb200_harvest *h);
  * fb200_forward / fb200_jacobian call on this model (CUDA events on the
  * model's stream), and how many kernels that call launched.                  */
 int fb200_last_kernel_ms(const fb200_model *model, double *ms, int *launches);
+/* How many observation points of the most recent fb200_forward / fb200_jacobian call were
+ * re-evaluated by the per-cell kernels because they lie in a wall that the reference rounds
+ * differently from its two sides (fb200_model_set_hazard_planes; mesher/mesh.py:447-456,
+ * 629-634) or meet the thickness-dependent shift of a merged relief node.          */
+int fb200_last_fallback_points(const fb200_model *model, int *points);
+
+/* Page-locked host memory (cudaHostAlloc) for result arrays that are written repeatedly, e.g.
+ * the host-resident sensitivity matrix of an inversion loop (eqlayer.py:100-111 rebuilds it per
+ * call): fb200_jacobian streams into it at PCIe DMA speed.  Not needed for correctness.       */
+int fb200_host_alloc(size_t bytes, void **ptr);
+int fb200_host_free(void *ptr);
 /* Register-resident DFMA-chain microbenchmark: the FP64 roofline denominator
  * that MEASURED_PEAKS.json does not carry.  Runs for about `seconds`, returns
  * the best (burst) and the whole-run (sustained) rate in TFLOP/s (DFMA = 2). */

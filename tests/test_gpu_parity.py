@@ -426,14 +426,27 @@ def test_hazard_walls_send_merged_forms_to_the_per_cell_kernels(gpu_lib):
         assert not np.array_equal(a['gyy'], b['gyy'])
         ja, jb = geo.jacobian(xp, yp, zp, 'gyy'), geo.jacobian(xp, yp, zp, 'gyy', per_cell=True)
         assert not np.array_equal(ja, jb)
-        # one point exactly in a mismatched wall: everything falls back
+        # one point exactly in a mismatched wall: THAT point is re-evaluated per cell (same bits
+        # as a per-cell call), every other point keeps its merged-form value
         yp2 = yp.copy()
         yp2[7] = hazard_y[0]
-        a = fwd.fields(xp, yp2, zp, ['gz', 'gyy'])
-        b = fwd.fields(xp, yp2, zp, ['gz', 'gyy'], per_cell=True)
-        for f in a:
-            assert np.array_equal(a[f], b[f]), f
-        assert np.array_equal(geo.jacobian(xp, yp2, zp, 'gyy'), geo.jacobian(xp, yp2, zp, 'gyy', per_cell=True))
+        others = np.arange(xp.size) != 7
+        a2 = fwd.fields(xp, yp2, zp, ['gz', 'gyy'])
+        assert fwd.last_fallback_points() == 1
+        b2 = fwd.fields(xp[7:8].copy(), yp2[7:8].copy(), zp[7:8].copy(), ['gz', 'gyy'], per_cell=True)
+        for f in a2:
+            assert a2[f][7] == b2[f][0], f
+            assert np.array_equal(a2[f][others], a[f][others]), f
+        for transposed in (False, True):
+            j2 = geo.jacobian(xp, yp2, zp, 'gyy', transposed=transposed)
+            assert geo.last_fallback_points() == 1
+            jc = geo.jacobian(xp, yp2, zp, 'gyy', per_cell=True, transposed=transposed)
+            if transposed:
+                j2, jc = j2.T, jc.T
+            assert np.array_equal(j2[7], jc[7])
+            assert np.array_equal(j2[others], ja[others])
+        # several flagged points, on two axes' walls would be the same mechanism; the adjoint
+        # sums over the points and still falls back as a whole
         assert np.array_equal(geo.adjoint(xp, yp2, zp, data, 'gz'),
                               geo.adjoint(xp, yp2, zp, data, 'gz', per_cell=True))
 
@@ -470,15 +483,26 @@ def test_relief_surface_form_equals_per_cell_and_oracle(gpu_lib, oracle):
                               oracle.condition('gz', xp, yp, zp, flat.bounds, flat.density[:, None]),
                               C_FLOOR_FAST, 'relief surface gz alone')
             # points IN the reference plane on grid lines through the rim nodes: gxz / gyz need a
-            # cell's own thickness there -> the call evaluates per cell (bit-identical to it)
+            # cell's own thickness there -> those points are re-evaluated per cell (bit-identical
+            # to a per-cell call), the others keep the surface form
             sf = model.surface
             xp = np.repeat(sf.nodes[0][:2], 3)
             yp = np.repeat(sf.nodes[1][:2], 3) + np.tile([7000., -9000., 12000.], 2)
             zp = np.zeros(6)
             a = model.fields(xp, yp, zp, ['gxz', 'gyz', 'gz'])
-            b = model.fields(xp, yp, zp, ['gxz', 'gyz', 'gz'], per_cell=True)
+            k = model.last_fallback_points()
+            assert 1 <= k <= 6
+            same = np.ones(6, dtype=bool)
+            for i in range(6):
+                b = model.fields(xp[i:i + 1].copy(), yp[i:i + 1].copy(), zp[i:i + 1].copy(),
+                                 ['gxz', 'gyz', 'gz'], per_cell=True)
+                for f in a:
+                    same[i] &= a[f][i] == b[f][0]
             for f in a:
-                assert np.array_equal(a[f], b[f]), f
+                ref = oracle.model(f, xp, yp, zp, flat.bounds, flat.density[:, None])
+                cond = oracle.condition(f, xp, yp, zp, flat.bounds, flat.density[:, None])
+                assert_parity(a[f], ref, cond, C_FLOOR_FAST, 'relief, points in the reference plane ' + f)
+            assert same.sum() >= k
     # the drop-in functions use it too, and an override bypasses it
     xp, yp, zp = gridder.regular(area, (9, 8), z=-1200.)
     got = prism.gz(xp, yp, zp, relief)
@@ -510,6 +534,65 @@ def test_relief_at_c5_scale(gpu_lib, oracle):
         cond = oracle.condition(f, xp, yp, zp, flat.bounds, flat.density[:, None], threads=8)
         assert_parity(surf[f], ref, cond, C_FLOOR_FAST, 'C5 surface ' + f)
         assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'C5 per cell ' + f)
+
+
+def test_c2_at_full_model_size(gpu_lib, oracle):
+    """The benchmarked config itself (BASELINE config 2: six tensor components of the 50x50x20
+    variable-density mesh) at its FULL model size on 48 of its 200x200 points, node sharing and
+    per cell, against the oracle; the same for the grid whose lines lie in mesh planes."""
+    import bench
+    from fatiando_b200 import prism
+    from fatiando_b200.flatten import flatten
+    for name in ("c2", "c2a"):
+        w = bench.make_workload(name, 1)
+        idx = np.linspace(0, w['xp'].size - 1, 48).astype(int)
+        xp, yp, zp = (np.ascontiguousarray(w[k][idx]) for k in ('xp', 'yp', 'zp'))
+        flat = flatten(w['model'], 'density')
+        with prism.Model(flat, 'density') as model:
+            assert model.nodes is not None and model.size == 50000
+            nodes = model.fields(xp, yp, zp, w['names'])
+            cells = model.fields(xp, yp, zp, w['names'], per_cell=True)
+        worst = 0.0
+        for f in w['names']:
+            ref = oracle.model(f, xp, yp, zp, flat.bounds, flat.density[:, None], threads=8)
+            cond = oracle.condition(f, xp, yp, zp, flat.bounds, flat.density[:, None], threads=8)
+            worst = max(worst, assert_parity(nodes[f], ref, cond, C_FLOOR_FAST, '%s nodes %s' % (name, f)))
+            assert_parity(cells[f], ref, cond, C_FLOOR_FAST, '%s per cell %s' % (name, f))
+        assert worst < 0.5          # observed: a few hundredths of the floor
+
+
+def test_borehole_points_on_lines_through_mesh_nodes(gpu_lib, oracle):
+    """Points INSIDE a regular mesh on vertical lines through its nodes (borehole data), some
+    of them exactly at nodes.  With walls that the reference rounds the same way from both
+    sides, every cell around such a line sees the same zero offsets, safe_atan2(0, 0) = 0 and
+    safe_log(0) = 0 apply alike, and the node-sharing sum is the reference's regrouped: under
+    the floor, like the per-cell kernels.  (Walls rounded differently are hazard walls: the
+    call runs per cell, test_hazard_walls_send_merged_forms_to_the_per_cell_kernels.)"""
+    from fatiando_b200 import prism, mesher, utils
+    from fatiando_b200.flatten import flatten
+    rs = np.random.RandomState(31)
+    mesh = mesher.PrismMesh((0, 5000, 0, 4000, 0, 2000), (8, 8, 10))       # 500 / 500 / 250 m, exact
+    mesh.addprop('density', rs.uniform(-1000, 1000, mesh.size))
+    mesh.addprop('magnetization', rs.uniform(-2, 2, (mesh.size, 3)))
+    zs = np.concatenate([np.linspace(-100, 2100, 23), [250.0, 1000.0, 0.0, 2000.0]])
+    lines = [(1500.0, 2000.0), (0.0, 0.0), (5000.0, 4000.0), (2500.0, 500.0), (2500.0, 730.0)]
+    xp = np.concatenate([np.full(zs.size, x) for x, _ in lines])
+    yp = np.concatenate([np.full(zs.size, y) for _, y in lines])
+    zp = np.tile(zs, len(lines))
+    fv = utils.dircos(30, -15)
+    for prop, names in (('density', GRAV), ('magnetization', MAG)):
+        flat = flatten(mesh, prop)
+        assert flat.nodes is not None and all(h.size == 0 for h in flat.nodes.hazard)
+        props = flat.density[:, None] if prop == 'density' else flat.magnetization
+        with prism.Model(mesh, prop) as model:
+            nodes = model.fields(xp, yp, zp, names, fvec=fv)
+            cells = model.fields(xp, yp, zp, names, fvec=fv, per_cell=True)
+        for f in names:
+            pr = props if f != 'tf' else np.hstack([props, np.tile(fv, (props.shape[0], 1))])
+            ref = oracle.model(f, xp, yp, zp, flat.bounds, pr)
+            cond = oracle.condition(f, xp, yp, zp, flat.bounds, pr)
+            assert_parity(nodes[f], ref, cond, C_FLOOR_FAST, 'borehole nodes ' + f)
+            assert_parity(cells[f], ref, cond, C_FLOOR_FAST, 'borehole per cell ' + f)
 
 
 def test_c3_and_c4_at_full_model_size(gpu_lib, oracle):
