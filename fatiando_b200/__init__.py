@@ -11,6 +11,7 @@ kernel ``_prism``, the prism meshes that feed it, and the dense sensitivity
 * :mod:`fatiando_b200.mesher`  -- ``Prism``, ``PrismMesh``, ``PrismRelief``
 * :mod:`fatiando_b200.flatten` -- mesh -> SoA arrays
 * :mod:`fatiando_b200.partition` -- observation / prism sharding over GPUs
+* :mod:`fatiando_b200.normal`  -- Gauss-Newton products (J^T W J, J^T W r, J p) on a device-resident J
 * :mod:`fatiando_b200.harvester` -- drop-in for ``fatiando.gravmag.harvester`` (planting
   inversion) on a device-resident effect engine
 * :mod:`fatiando_b200.sphere`  -- drop-in for ``fatiando.gravmag.sphere`` (sibling kernel)
@@ -23,7 +24,7 @@ implementation behind it.
 """
 from . import constants, gridder, mesher, utils          # noqa: F401
 from . import flatten, prism, _prism, partition          # noqa: F401
-from . import harvester, sphere, polyprism, imaging      # noqa: F401
+from . import harvester, sphere, polyprism, imaging, normal   # noqa: F401
 from .mesher import Prism, PrismMesh, PrismRelief, Sphere, PolygonalPrism    # noqa: F401
 from ._lib import pinned_empty                            # noqa: F401
 

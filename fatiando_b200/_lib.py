@@ -65,6 +65,16 @@ _SIGNATURES = {
     "fb200_last_kernel_ms": ([ctypes.c_void_p, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int)],
                              ctypes.c_int),
     "fb200_last_fallback_points": ([ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)], ctypes.c_int),
+    "fb200_gram": ([ctypes.c_int, ctypes.c_void_p, _i64, _i64, _i64, ctypes.c_void_p, _d, ctypes.c_void_p,
+                    _i64, ctypes.POINTER(_d)], ctypes.c_int),
+    "fb200_matvec": ([ctypes.c_int, ctypes.c_void_p, _i64, _i64, _i64, ctypes.c_void_p, ctypes.c_void_p],
+                     ctypes.c_int),
+    "fb200_matvec_t": ([ctypes.c_int, ctypes.c_void_p, _i64, _i64, _i64, ctypes.c_void_p, ctypes.c_void_p,
+                        _d, ctypes.c_void_p], ctypes.c_int),
+    "fb200_device_alloc": ([ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
+    "fb200_device_free": ([ctypes.c_int, ctypes.c_void_p], ctypes.c_int),
+    "fb200_copy": ([ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int],
+                   ctypes.c_int),
     "fb200_host_alloc": ([ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)], ctypes.c_int),
     "fb200_host_free": ([ctypes.c_void_p], ctypes.c_int),
     "fb200_fp64_peak": ([ctypes.c_int, _d, ctypes.POINTER(_d), ctypes.POINTER(_d)], ctypes.c_int),

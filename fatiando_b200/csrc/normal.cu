@@ -1,0 +1,310 @@
+// normal.cu -- consumers of a DEVICE-RESIDENT sensitivity matrix: the Gauss-Newton products of
+// fatiando/inversion/misfit.py on a row block of J.
+//
+//   fb200_gram      G = factor * J^T diag(w) J      (misfit.py:250-256: hessian = 2 J^T W J)
+//   fb200_matvec    y = J p                         (misfit.py: predicted data of a linear problem)
+//   fb200_matvec_t  g = factor * J^T (w .* r)       (misfit.py:280-294: gradient = -2 J^T W r)
+//
+// J is (n x m), C-order, row = observation (the layout fb200_jacobian writes, eqlayer.py:108-111);
+// on several GPUs every rank owns a row block (partition.jacobian_row_sharded) and G, g are summed
+// with ONE all-reduce (partition.gram_row_sharded) -- the one place on this path where a
+// collective moves real data (12.8 GB for the 40 000^2 matrix of config C4).
+//
+// The Gram matrix is a rank-n update: 2*n*m^2/2 FLOP on n*m*8 bytes -- at C4 (n = 31 250 per GPU,
+// m = 40 000) 1 250 FLOP per byte, FP64-pipe-bound.  gram_kernel is a register-tiled fp64 SYRK:
+// a 128 x 128 tile of G per block of 256 threads, 8 x 8 accumulators per thread, the two 16-row
+// panels of J staged through a three-stage cp.async ring (8-byte copies, zero-filled past the
+// matrix edges, so any n, m and leading dimension work); only tiles on or above the diagonal are
+// computed, mirror_kernel fills the rest.  Per 16-row step a thread issues 64 DFMA per 8
+// 16-byte shared-memory loads (conflict-free: a column pair per lane, 32 columns apart).
+// There is no fp64 tcgen05 path; the B200's FP64 rate is the DFMA rate.
+#include <algorithm>
+#include <cstdint>
+#include <string>
+
+#include "../../include/fatiando_b200.h"
+#include "abi_internal.h"
+
+namespace fb200 {
+
+constexpr int GT = 128;          // tile of G (rows and columns)
+constexpr int GK = 16;           // rows of J per stage
+constexpr int GTHREADS = 256;
+constexpr int GSTAGES = 3;
+
+struct GramArgs {
+    const double *J;
+    const double *w;             // row weights or nullptr
+    int64_t n, m, ld;
+    double factor;
+    double *G;
+    int64_t ldg;
+    int tiles;                   // tiles per side
+};
+
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src, bool valid)
+{
+    const int bytes = valid ? 8 : 0;            // src-size 0: the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    // stage s: A panel [GK][GT], B panel [GK][GT], weights [GK]
+    constexpr int STAGE = 2 * GK * GT + GK;
+    // upper-triangular tile (bi <= bj) from the linear block index
+    int bi = 0, rest = (int)blockIdx.x;
+    while (rest >= a.tiles - bi) { rest -= a.tiles - bi; ++bi; }
+    const int bj = bi + rest;
+    const int64_t qa = (int64_t)bi * GT, qb = (int64_t)bj * GT;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    const int ktiles = (int)((a.n + GK - 1) / GK);
+    auto issue = [&](int t) {
+        const int s = t % GSTAGES;
+        const int64_t l0 = (int64_t)t * GK;
+        const unsigned dst = sbase + (unsigned)(s * STAGE) * 8u;
+#pragma unroll
+        for (int i = 0; i < (GK * GT) / GTHREADS; ++i) {
+            const int e = tid + i * GTHREADS;
+            const int r = e / GT, c = e % GT;
+            const int64_t l = l0 + r;
+            const bool row_ok = l < a.n;
+            const double *row = a.J + (row_ok ? l : 0) * a.ld;
+            cp_async8(dst + (unsigned)e * 8u, row + (qa + c < a.m ? qa + c : 0), row_ok && qa + c < a.m);
+            cp_async8(dst + (unsigned)(GK * GT + e) * 8u, row + (qb + c < a.m ? qb + c : 0), row_ok && qb + c < a.m);
+        }
+        if (WEIGHTED && tid < GK) {
+            const int64_t l = l0 + tid;
+            cp_async8(dst + (unsigned)(2 * GK * GT + tid) * 8u, a.w + (l < a.n ? l : 0), l < a.n);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int t = 0; t < GSTAGES - 1; ++t) {
+        if (t < ktiles) issue(t);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int t = 0; t < ktiles; ++t) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(GSTAGES - 2) : "memory");
+        __syncthreads();                                   // stage t has landed, stage t-1 is free
+        if (t + GSTAGES - 1 < ktiles) issue(t + GSTAGES - 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const double *As = smem + (t % GSTAGES) * STAGE;
+        const double *Bs = As + GK * GT;
+        const double *Ws = Bs + GK * GT;
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            double av[8], bv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 v = *reinterpret_cast<const double2 *>(As + k * GT + ty * 2 + 32 * i);
+                av[2 * i] = v.x; av[2 * i + 1] = v.y;
+                const double2 u = *reinterpret_cast<const double2 *>(Bs + k * GT + tx * 2 + 32 * i);
+                bv[2 * i] = u.x; bv[2 * i + 1] = u.y;
+            }
+            if (WEIGHTED) {
+                const double wk = Ws[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bv[j] *= wk;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+    }
+    // this thread's rows {ty*2 + 32 i + (0,1)} and columns {tx*2 + 32 j + (0,1)} of the tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t row = qa + ty * 2 + 32 * (i >> 1) + (i & 1);
+        if (row >= a.m) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t col = qb + tx * 2 + 32 * (j >> 1) + (j & 1);
+            if (col < a.m) a.G[row * a.ldg + col] = acc[i][j] * a.factor;
+        }
+    }
+}
+
+// G[j][i] = G[i][j] for i < j, 32 x 32 tiles through shared memory
+__global__ void mirror_kernel(double *G, int64_t m, int64_t ldg)
+{
+    __shared__ double t[32][33];
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    const int64_t r0 = bi * 32, c0 = bj * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t row = r0 + r, col = c0 + threadIdx.x;
+        t[r][threadIdx.x] = (row < m && col < m) ? G[row * ldg + col] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t row = c0 + r, col = r0 + threadIdx.x;       // transposed position
+        if (row < m && col < m && col < row) G[row * ldg + col] = t[threadIdx.x][r];
+    }
+}
+
+// y[l] = sum_q J[l][q] p[q]: one warp per row, fixed-order lane sums then a shuffle tree
+__global__ void matvec_kernel(const double *J, int64_t n, int64_t m, int64_t ld, const double *p, double *y)
+{
+    const int64_t l = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (l >= n) return;
+    const int lane = threadIdx.x & 31;
+    const double *row = J + l * ld;
+    double s = 0.0;
+    for (int64_t q = lane; q < m; q += 32) s = fma(row[q], p[q], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[l] = s;
+}
+
+// part[c][q] = sum over the rows of chunk c of J[l][q] * (w[l] r[l]); thread = column
+__global__ void matvec_t_kernel(const double *J, int64_t n, int64_t m, int64_t ld, const double *r,
+                                const double *w, int64_t rows_per_chunk, double *part)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const int64_t l0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t l1 = l0 + rows_per_chunk < n ? l0 + rows_per_chunk : n;
+    double s = 0.0;
+    for (int64_t l = l0; l < l1; ++l) s = fma(J[l * ld + q], w ? w[l] * r[l] : r[l], s);
+    part[(int64_t)blockIdx.y * m + q] = s;
+}
+
+__global__ void sum_chunks_kernel(const double *part, int64_t m, int chunks, double factor, double *g)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * m + q];
+    g[q] = s * factor;
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" int fb200_gram(int device, const double *J, int64_t n, int64_t m, int64_t ld, const double *w,
+                          double factor, double *G, int64_t ldg, double *ms)
+{
+    if (n < 0 || m < 0) return set_error(FB200_EINVAL, "negative matrix size");
+    if (m > 0 && (!G || ldg < m)) return set_error(FB200_EINVAL, "G is NULL or ldg < m");
+    if (n > 0 && m > 0 && (!J || ld < m)) return set_error(FB200_EINVAL, "J is NULL or ld < m");
+    if (m == 0) return FB200_OK;
+    DeviceScope scope(device);
+    if (!scope.ok) return set_error(FB200_ECUDA, "cudaSetDevice failed");
+    GramArgs a;
+    a.J = J; a.w = w; a.n = n; a.m = m; a.ld = ld; a.factor = factor; a.G = G; a.ldg = ldg;
+    a.tiles = (int)((m + GT - 1) / GT);
+    const int64_t blocks = (int64_t)a.tiles * (a.tiles + 1) / 2;
+    if (blocks > 2147483647ll) return set_error(FB200_EUNSUP, "matrix too large for one launch");
+    const size_t smem = (size_t)GSTAGES * (2 * GK * GT + GK) * sizeof(double);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms) {
+        FB_CK(cudaEventCreate(&e0));
+        FB_CK(cudaEventCreate(&e1));
+        FB_CK(cudaEventRecord(e0, 0));
+    }
+    if (w) {
+        FB_CK(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_kernel<true><<<(unsigned)blocks, GTHREADS, smem>>>(a);
+    } else {
+        FB_CK(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_kernel<false><<<(unsigned)blocks, GTHREADS, smem>>>(a);
+    }
+    FB_CK(cudaGetLastError());
+    const unsigned mt = (unsigned)((m + 31) / 32);
+    mirror_kernel<<<dim3(mt, mt), dim3(32, 8)>>>(G, m, ldg);
+    FB_CK(cudaGetLastError());
+    if (ms) {
+        FB_CK(cudaEventRecord(e1, 0));
+        FB_CK(cudaEventSynchronize(e1));
+        float t = 0.f;
+        FB_CK(cudaEventElapsedTime(&t, e0, e1));
+        *ms = t;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    } else {
+        FB_CK(cudaDeviceSynchronize());
+    }
+    return FB200_OK;
+}
+
+extern "C" int fb200_matvec(int device, const double *J, int64_t n, int64_t m, int64_t ld, const double *p,
+                            double *y)
+{
+    if (n < 0 || m < 0 || (n > 0 && (!J || !y || ld < m)) || (m > 0 && !p))
+        return set_error(FB200_EINVAL, "bad argument to fb200_matvec");
+    if (n == 0) return FB200_OK;
+    DeviceScope scope(device);
+    if (!scope.ok) return set_error(FB200_ECUDA, "cudaSetDevice failed");
+    matvec_kernel<<<(unsigned)((n + 7) / 8), 256>>>(J, n, m, ld, p, y);
+    FB_CK(cudaGetLastError());
+    FB_CK(cudaDeviceSynchronize());
+    return FB200_OK;
+}
+
+extern "C" int fb200_matvec_t(int device, const double *J, int64_t n, int64_t m, int64_t ld, const double *r,
+                              const double *w, double factor, double *g)
+{
+    if (n < 0 || m < 0 || (m > 0 && !g) || (n > 0 && m > 0 && (!J || !r || ld < m)))
+        return set_error(FB200_EINVAL, "bad argument to fb200_matvec_t");
+    if (m == 0) return FB200_OK;
+    DeviceScope scope(device);
+    if (!scope.ok) return set_error(FB200_ECUDA, "cudaSetDevice failed");
+    // fixed chunks of rows, added in chunk order: reproducible
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(512, (n + 255) / 256));
+    const int64_t rows_per_chunk = (std::max<int64_t>(n, 1) + chunks - 1) / chunks;
+    double *part = nullptr;
+    FB_CK(cudaMallocAsync((void **)&part, (size_t)chunks * m * sizeof(double), 0));
+    matvec_t_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)chunks), 256>>>(J, n, m, ld, r, w,
+                                                                                  rows_per_chunk, part);
+    FB_CK(cudaGetLastError());
+    sum_chunks_kernel<<<(unsigned)((m + 255) / 256), 256>>>(part, m, chunks, factor, g);
+    FB_CK(cudaGetLastError());
+    FB_CK(cudaFreeAsync(part, 0));
+    FB_CK(cudaDeviceSynchronize());
+    return FB200_OK;
+}
+
+// plain device buffers for callers without a tensor library (the ctypes binding)
+extern "C" int fb200_device_alloc(int device, size_t bytes, void **ptr)
+{
+    if (!ptr) return set_error(FB200_EINVAL, "ptr is NULL");
+    *ptr = nullptr;
+    DeviceScope scope(device);
+    if (!scope.ok) return set_error(FB200_ECUDA, "cudaSetDevice failed");
+    FB_CK(cudaMalloc(ptr, bytes ? bytes : 1));
+    return FB200_OK;
+}
+
+extern "C" int fb200_device_free(int device, void *ptr)
+{
+    DeviceScope scope(device);
+    if (!scope.ok) return set_error(FB200_ECUDA, "cudaSetDevice failed");
+    if (ptr) FB_CK(cudaFree(ptr));
+    return FB200_OK;
+}
+
+// kind: 0 host -> device, 1 device -> host, 2 device -> device (synchronous)
+extern "C" int fb200_copy(int device, void *dst, const void *src, size_t bytes, int kind)
+{
+    if (bytes && (!dst || !src)) return set_error(FB200_EINVAL, "NULL pointer");
+    if (kind < 0 || kind > 2) return set_error(FB200_EINVAL, "kind must be 0, 1 or 2");
+    DeviceScope scope(device);
+    if (!scope.ok) return set_error(FB200_ECUDA, "cudaSetDevice failed");
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost
+                                                                            : cudaMemcpyDeviceToDevice;
+    FB_CK(cudaMemcpy(dst, src, bytes, k));
+    return FB200_OK;
+}

@@ -75,8 +75,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 }
 
 // Eval::template pair<MASK>(acc, xp, yp, zp, x1, x2, y1, y2, z1, z2, p0, p1, p2, f)
+// Component sets whose evaluators keep more than ~60 doubles live (all ten gravity fields, the
+// potential with its nine products, gx+gy+gz) get 168 registers (3 blocks per SM) instead of
+// spilling at 128; measured neutral to +3 % for them, and the local-memory traffic is gone.
+constexpr int fwd_min_blocks(uint32_t mask)
+{
+    return (mask == 0x3FFu || mask == 0x3FEu || mask == 0x001u || mask == 0x00Eu) ? 3 : FB200_FWD_MIN_BLOCKS;
+}
+
 template <uint32_t MASK, class Eval>
-__global__ void __launch_bounds__(FWD_THREADS, FB200_FWD_MIN_BLOCKS)
+__global__ void __launch_bounds__(FWD_THREADS, fwd_min_blocks(MASK))
 forward_kernel(const ForwardArgs a)
 {
     constexpr int NC = popc(MASK);

@@ -312,6 +312,61 @@ def adjoint_point_sharded(xp, yp, zp, prisms, data, field='gz', pmag=None, fvec=
     return total.cpu().numpy()
 
 
+def gram_row_sharded(xp, yp, zp, prisms, field='gz', weights=None, residual=None, factor=1.0,
+                     pmag=None, fvec=None, device=None, to_host=True):
+    """
+    The normal-equation pieces of a row-sharded sensitivity matrix (the Gauss-Newton step of
+    ``fatiando.inversion``: ``Misfit.hessian`` = ``2 J^T W J``, misfit.py:250-256, and
+    ``Misfit.gradient`` = ``-2 J^T W r``, misfit.py:280-294): every rank builds the rows of ITS
+    observation points in HBM (:class:`fatiando_b200.normal.SensitivityBlock`), forms
+    ``factor * J_r^T W_r J_r`` with the fp64 SYRK kernel and -- when ``residual`` is given --
+    ``J_r^T W_r r_r``; ONE all-reduce each (NCCL over NVLink, on the GPU tensors) adds the ranks'
+    contributions.  This is the one exchange on this path that moves real data: the full
+    ``(ncells, ncells)`` fp64 matrix (12.8 GB at config C4).
+
+    Returns ``(G, g, timings)``: numpy arrays (``to_host=True``) or CUDA tensors; ``g`` is None
+    without a residual.  ``timings``: build / gram kernel / collective milliseconds, bytes.
+    """
+    import torch
+    from .normal import SensitivityBlock
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    flat = prisms if isinstance(prisms, FlatModel) else flatten(prisms, None, override=True)
+    sl = local_slice(xp.size, rank, world)
+    dev_index = default_device(rank) if device is None else device
+    dev = torch.device('cuda', dev_index)
+    w_local = None if weights is None else np.ascontiguousarray(weights[sl], dtype=np.float64)
+    with _prism_api.Model(flat, None, device=dev_index) as model:
+        block = SensitivityBlock(model, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
+                                 np.ascontiguousarray(zp[sl]), field, pmag=pmag, fvec=fvec)
+    try:
+        G_dev = block.gram_device(w_local, factor)
+        timings = {"build_ms": block.build_ms, "gram_ms": block.last_ms}
+        G = torch.as_tensor(G_dev, device=dev)             # zero-copy view (__cuda_array_interface__)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(G, op=dist.ReduceOp.SUM)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        timings.update(collective_ms=e0.elapsed_time(e1), collective_bytes=G.numel() * 8)
+        g = None
+        if residual is not None:
+            g_local = block.tdot(np.ascontiguousarray(residual[sl], dtype=np.float64), w_local, 1.0)
+            g = torch.from_numpy(g_local).to(dev)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        if to_host:
+            G_out = G.cpu().numpy()
+            g_out = None if g is None else g.cpu().numpy()
+        else:
+            G_out, g_out = G.clone(), g
+        del G
+        G_dev.close()
+        return G_out, g_out, timings
+    finally:
+        block.close()
+
+
 def fields_multi_device(xp, yp, zp, prisms, names, devices, dens=None, pmag=None, fvec=None,
                         **kw):
     """

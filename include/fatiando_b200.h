@@ -312,6 +312,32 @@ int fb200_harvest_predicted(fb200_harvest *h, float *out /* all data sets */);
 int fb200_harvest_effect(fb200_harvest *h, int64_t row, double *out /* all data sets */);
 int64_t fb200_harvest_launches(const fb200_harvest *h);
 
+/* ---- consumers of a device-resident sensitivity matrix --------------------
+ * The Gauss-Newton products of fatiando/inversion/misfit.py on a ROW BLOCK of J that stays in
+ * HBM (fb200_jacobian with FB200_DEVICE_POINTERS; rows = this GPU's observations).  All
+ * pointers are device pointers on `device`; J is (n x m) C-order with leading dimension ld.
+ *
+ * fb200_gram:     G = factor * J^T diag(w) J, (m x m) C-order, full symmetric matrix.
+ *                 Replaces `safe_dot(jacobian.T, self.weights*jacobian)` and the factor
+ *                 2*regul_param of Misfit.hessian (misfit.py:250-256).  w may be NULL.
+ *                 *ms (optional) receives the device time of the kernels.
+ * fb200_matvec:   y = J p (the predicted data of a linear problem, misfit.py `predicted`).
+ * fb200_matvec_t: g = factor * J^T (w .* r); Misfit.gradient (misfit.py:280-294) with
+ *                 factor = -2*regul_param.  w may be NULL.
+ * Row blocks of several GPUs are combined by one all-reduce of G / g
+ * (fatiando_b200/partition.py: gram_row_sharded).                                  */
+int fb200_gram(int device, const double *J, int64_t n, int64_t m, int64_t ld, const double *w,
+               double factor, double *G, int64_t ldg, double *ms);
+int fb200_matvec(int device, const double *J, int64_t n, int64_t m, int64_t ld, const double *p,
+                 double *y);
+int fb200_matvec_t(int device, const double *J, int64_t n, int64_t m, int64_t ld, const double *r,
+                   const double *w, double factor, double *g);
+/* Plain device buffers and synchronous copies for bindings without a tensor library
+ * (kind: 0 host->device, 1 device->host, 2 device->device).                        */
+int fb200_device_alloc(int device, size_t bytes, void **ptr);
+int fb200_device_free(int device, void *ptr);
+int fb200_copy(int device, void *dst, const void *src, size_t bytes, int kind);
+
 /* ---- measurement helpers (used by bench.py; not part of the data path) --
  * Device time in milliseconds of the kernels launched by the most recent
  * fb200_forward / fb200_jacobian call on this model (CUDA events on the
