@@ -15,8 +15,11 @@
 // a 128 x 128 tile of G per block of 256 threads, 8 x 8 accumulators per thread, the two 16-row
 // panels of J staged through a three-stage cp.async ring (8-byte copies, zero-filled past the
 // matrix edges, so any n, m and leading dimension work); only tiles on or above the diagonal are
-// computed, mirror_kernel fills the rest.  Per 16-row step a thread issues 64 DFMA per 8
-// 16-byte shared-memory loads (conflict-free: a column pair per lane, 32 columns apart).
+// computed, mirror_kernel fills the rest.  Per row of J a thread issues 64 DFMA per 8 16-byte
+// shared-memory loads (a warp's A loads are broadcasts, its B loads 256 contiguous bytes).
+// Measured: 70 % of the DFMA peak; 16 warps of 8 x 4 accumulators give the same (the limit is the
+// register-operand bandwidth of three-register DFMAs, 90 % in tools/fp64_pipe_probe.cu, times
+// the issue slots of the loads).
 // There is no fp64 tcgen05 path; the B200's FP64 rate is the DFMA rate.
 #include <algorithm>
 #include <cstdint>
@@ -29,7 +32,7 @@ namespace fb200 {
 
 constexpr int GT = 128;          // tile of G (rows and columns)
 constexpr int GK = 16;           // rows of J per stage
-constexpr int GTHREADS = 256;
+constexpr int GTHREADS = 256;     // 8 warps, 8 x 8 accumulators per thread
 constexpr int GSTAGES = 3;
 
 struct GramArgs {
@@ -47,19 +50,60 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void *src, bool va
     const int bytes = valid ? 8 : 0;            // src-size 0: the destination is zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, int bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
 
-template <bool WEIGHTED>
+// Tile (bi <= bj) of a linear block index.  Blocks that run at the same time should share panels
+// of J in L2: the upper triangle is walked in SUPER x SUPER groups of tiles (a group's ~100
+// resident blocks read SUPER + SUPER panels instead of one each).
+constexpr int SUPER = 12;
+__device__ __forceinline__ void tile_of(int64_t id, int tiles, int *bi, int *bj)
+{
+    const int ns = (tiles + SUPER - 1) / SUPER;          // super-tiles per side
+    // super-tile rows: row I holds (ns - I) super-tiles; diagonal ones are triangles
+    int I = 0;
+    for (;; ++I) {
+        const int rows = min(SUPER, tiles - I * SUPER);
+        // tiles in super-row I: diagonal super-tile (triangle) + full ones to the right
+        const int64_t diag = (int64_t)rows * (rows + 1) / 2;
+        const int64_t right = (int64_t)rows * (tiles - (I * SUPER + rows));
+        if (id < diag + right) {
+            if (id < diag) {                               // inside the diagonal super-tile
+                int r = 0;
+                while (id >= rows - r) { id -= rows - r; ++r; }
+                *bi = I * SUPER + r;
+                *bj = I * SUPER + r + (int)id;
+            } else {
+                id -= diag;
+                // full super-tiles to the right, SUPER columns each (the last one may be narrower)
+                const int64_t per = (int64_t)rows * SUPER;
+                const int Jx = (int)(id / per);
+                const int64_t in = id - (int64_t)Jx * per;
+                const int c0 = I * SUPER + rows + Jx * SUPER;
+                const int cols = min(SUPER, tiles - c0);
+                *bi = I * SUPER + (int)(in / cols);
+                *bj = c0 + (int)(in % cols);
+            }
+            return;
+        }
+        id -= diag + right;
+    }
+}
+
+template <bool WEIGHTED, bool VEC>
 __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     // stage s: A panel [GK][GT], B panel [GK][GT], weights [GK]
     constexpr int STAGE = 2 * GK * GT + GK;
-    // upper-triangular tile (bi <= bj) from the linear block index
-    int bi = 0, rest = (int)blockIdx.x;
-    while (rest >= a.tiles - bi) { rest -= a.tiles - bi; ++bi; }
-    const int bj = bi + rest;
+    int bi, bj;
+    tile_of((int64_t)blockIdx.x, a.tiles, &bi, &bj);
     const int64_t qa = (int64_t)bi * GT, qb = (int64_t)bj * GT;
     const int tid = threadIdx.x;
+    // 16 row groups x 16 column groups; a warp = two row groups x 16 column groups, so that its
+    // A loads hit two addresses (broadcast) and its B loads 256 contiguous bytes
     const int ty = tid >> 4, tx = tid & 15;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
 
@@ -70,25 +114,56 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
     const int ktiles = (int)((a.n + GK - 1) / GK);
+    // Loader.  VEC: 16-byte copies, a thread owns the column pair c2 of rows r0, r0 + 4, ..
+    // (ld and m even, J 16-byte aligned); otherwise 8-byte copies, any layout.  Column validity
+    // is fixed per thread; row validity only matters in the last stage.
+    constexpr int PER = VEC ? (GK * GT / 2) / GTHREADS : (GK * GT) / GTHREADS;     // copies per panel
+    constexpr int RSTEP = VEC ? GTHREADS / (GT / 2) : GTHREADS / GT;               // rows between copies
+    const int r0 = VEC ? tid / (GT / 2) : tid / GT;
+    const int c0 = VEC ? (tid % (GT / 2)) * 2 : tid % GT;
+    const int a_bytes = VEC ? (qa + c0 + 1 < a.m ? 16 : (qa + c0 < a.m ? 8 : 0)) : (qa + c0 < a.m ? 8 : 0);
+    const int b_bytes = VEC ? (qb + c0 + 1 < a.m ? 16 : (qb + c0 < a.m ? 8 : 0)) : (qb + c0 < a.m ? 8 : 0);
+    const double *pa = a.J + (int64_t)r0 * a.ld + (a_bytes ? qa + c0 : 0);
+    const double *pb = a.J + (int64_t)r0 * a.ld + (b_bytes ? qb + c0 : 0);
+    const int64_t row_step = (int64_t)RSTEP * a.ld, stage_step = (int64_t)GK * a.ld;
+    const unsigned d0 = (unsigned)(r0 * GT + c0) * 8u;
     auto issue = [&](int t) {
-        const int s = t % GSTAGES;
-        const int64_t l0 = (int64_t)t * GK;
-        const unsigned dst = sbase + (unsigned)(s * STAGE) * 8u;
+        const unsigned dst = sbase + (unsigned)((t % GSTAGES) * STAGE) * 8u + d0;
+        const int64_t l0 = (int64_t)t * GK + r0;
+        const bool full = (int64_t)(t + 1) * GK <= a.n;
+        const double *ra = pa, *rb = pb;
+        if (VEC && full) {                      // the common case: no row predicates
 #pragma unroll
-        for (int i = 0; i < (GK * GT) / GTHREADS; ++i) {
-            const int e = tid + i * GTHREADS;
-            const int r = e / GT, c = e % GT;
-            const int64_t l = l0 + r;
-            const bool row_ok = l < a.n;
-            const double *row = a.J + (row_ok ? l : 0) * a.ld;
-            cp_async8(dst + (unsigned)e * 8u, row + (qa + c < a.m ? qa + c : 0), row_ok && qa + c < a.m);
-            cp_async8(dst + (unsigned)(GK * GT + e) * 8u, row + (qb + c < a.m ? qb + c : 0), row_ok && qb + c < a.m);
+            for (int i = 0; i < PER; ++i) {
+                const unsigned off = (unsigned)(i * RSTEP * GT) * 8u;
+                cp_async16(dst + off, ra, a_bytes);
+                cp_async16(dst + off + (unsigned)(GK * GT) * 8u, rb, b_bytes);
+                ra += row_step;
+                rb += row_step;
+            }
+        } else
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const bool ok = full || l0 + i * RSTEP < a.n;
+            const unsigned off = (unsigned)(i * RSTEP * GT) * 8u;
+            if (VEC) {
+                cp_async16(dst + off, ok ? ra : a.J, ok ? a_bytes : 0);
+                cp_async16(dst + off + (unsigned)(GK * GT) * 8u, ok ? rb : a.J, ok ? b_bytes : 0);
+            } else {
+                cp_async8(dst + off, ok ? ra : a.J, ok && a_bytes);
+                cp_async8(dst + off + (unsigned)(GK * GT) * 8u, ok ? rb : a.J, ok && b_bytes);
+            }
+            ra += row_step;
+            rb += row_step;
         }
         if (WEIGHTED && tid < GK) {
-            const int64_t l = l0 + tid;
-            cp_async8(dst + (unsigned)(2 * GK * GT + tid) * 8u, a.w + (l < a.n ? l : 0), l < a.n);
+            const int64_t l = (int64_t)t * GK + tid;
+            cp_async8(sbase + (unsigned)((t % GSTAGES) * STAGE + 2 * GK * GT + tid) * 8u,
+                      a.w + (l < a.n ? l : 0), l < a.n);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        pa += stage_step;
+        pb += stage_step;
     };
     for (int t = 0; t < GSTAGES - 1; ++t) {
         if (t < ktiles) issue(t);
@@ -215,13 +290,16 @@ extern "C" int fb200_gram(int device, const double *J, int64_t n, int64_t m, int
         FB_CK(cudaEventCreate(&e1));
         FB_CK(cudaEventRecord(e0, 0));
     }
-    if (w) {
-        FB_CK(cudaFuncSetAttribute(gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_kernel<true><<<(unsigned)blocks, GTHREADS, smem>>>(a);
-    } else {
-        FB_CK(cudaFuncSetAttribute(gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_kernel<false><<<(unsigned)blocks, GTHREADS, smem>>>(a);
-    }
+    // 16-byte copies need every row of J to start on a 16-byte boundary and pairs inside the row
+    const bool vec = (ld % 2 == 0) && (reinterpret_cast<uintptr_t>(J) % 16 == 0);
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<(unsigned)blocks, GTHREADS, smem>>>(a);
+        return cudaGetLastError();
+    };
+    if (w) FB_CK(vec ? go(gram_kernel<true, true>) : go(gram_kernel<true, false>));
+    else FB_CK(vec ? go(gram_kernel<false, true>) : go(gram_kernel<false, false>));
     FB_CK(cudaGetLastError());
     const unsigned mt = (unsigned)((m + 31) / 32);
     mirror_kernel<<<dim3(mt, mt), dim3(32, 8)>>>(G, m, ldg);
