@@ -59,6 +59,7 @@ WORK = {
     "c5": dict(flop=1478.0, what="gz"),
     "c5t": dict(flop=2850.0, what="gz + 6 tensor components"),
     "c4full": dict(flop=1478.0, what="Jacobian gz (+8 B stored per entry)"),
+    "c4a": dict(flop=1478.0, what="Jacobian gz on a commensurate grid (+8 B stored per entry)"),
     "c5full": dict(flop=1478.0, what="gz"),
     "c5tfull": dict(flop=2850.0, what="gz + 6 tensor components"),
     "c5tslab": dict(flop=2850.0, what="gz + 6 tensor components"),
@@ -147,6 +148,16 @@ def make_workload(name, world=1):
                     fvec=None, kind='jacobian',
                     label="C4: gz sensitivity matrix, %d rows (of 250000) x 40000 PrismMesh cells, "
                           "device-resident" % (rows * world))
+    if name == "c4a":
+        # C4's mesh with a level grid COMMENSURATE with it (40 m spacing = 1/5 of the 200 m cells,
+        # whole-metre coordinates): the opt-in kernel-value reuse of csrc/prism_grid_reuse.cuh.
+        # Every GPU builds the same 31626-row block (10.1 GB), like a C4 row block.
+        w = make_workload("c4", 1)
+        w['xp'], w['yp'], w['zp'] = gridder.regular((0, 10000, 0, 5000), (251, 126), z=-100)
+        w['kind'] = 'jacobian_grid'
+        w['label'] = ("C4 commensurate: gz sensitivity matrix, 251x126 level grid (40 m) x 40000 PrismMesh cells "
+                      "(200 m), device-resident, kernel values reused across points (opt-in grid_reuse)")
+        return w
     if name == "c4full":
         # the whole 250000 x 40000 sensitivity matrix (80 GB) resident on ONE B200, or its
         # row shards on several
@@ -466,6 +477,8 @@ class Bench(object):
         return self.models[key]
 
     def evaluation(self, model, w):
+        if w['kind'] == 'jacobian_grid':
+            return "grid"
         if model.nodes is not None:
             return "nodes"
         if model.surface is not None and w['kind'] == 'forward':
@@ -478,6 +491,8 @@ class Bench(object):
         from fatiando_b200.partition import local_slice
         w = make_workload(name, self.world if weak else 1)
         sl = local_slice(w['xp'].size, self.rank, self.world)
+        if w['kind'] == 'jacobian_grid':
+            sl = slice(0, w['xp'].size)            # the grid is the unit: every rank builds its own block
         xp, yp, zp = (np.ascontiguousarray(a[sl]) for a in (w['xp'], w['yp'], w['zp']))
         n = xp.size
         model, flat = self.model_of(w, model_key or name)
@@ -490,13 +505,24 @@ class Bench(object):
             mask |= 1 << i
         scale = np.array([prism.unit_scale(_lib.FIELDS[i]) for i in ids])
         fvec = None if w['fvec'] is None else np.ascontiguousarray(w['fvec'], dtype=np.float64)
-        shape = (n, m) if w['kind'] == 'jacobian' else (len(names), n)
+        shape = (n, m) if w['kind'].startswith('jacobian') else (len(names), n)
+        plan = None
+        if w['kind'] == 'jacobian_grid':
+            plan = prism.grid_plan(model.nodes, xp, yp, zp)
+            if plan is None:
+                raise SystemExit("workload %s: the grid is not commensurate with the mesh" % name)
+            plan['zc'] = np.ascontiguousarray(plan['zc'])
         d_out = torch.empty(shape, dtype=torch.float64, device=self.tdev)
         unit = np.array([1.0])
         torch.cuda.synchronize()
 
         def step_device():
-            if w['kind'] == 'jacobian':
+            if plan is not None:
+                rc = lib.fb200_jacobian_grid(model._handle, plan['ni'], plan['nj'], plan['kx'], plan['ky'],
+                                             _lib.dptr(plan['xu']), _lib.dptr(plan['yv']), _lib.dptr(plan['zc']),
+                                             ids[0], _lib.dptr(unit), _lib.dptr(fvec), float(scale[0]),
+                                             d_out.data_ptr(), m, _lib.DEVICE_POINTERS)
+            elif w['kind'] == 'jacobian':
                 rc = lib.fb200_jacobian(model._handle, d_pts[0].data_ptr(), d_pts[1].data_ptr(),
                                         d_pts[2].data_ptr(), n, ids[0], _lib.dptr(unit), _lib.dptr(fvec),
                                         float(scale[0]), d_out.data_ptr(), m, _lib.DEVICE_POINTERS)
@@ -533,7 +559,7 @@ class Bench(object):
         rows_done, d2h, e2e_s = n, 0, float('inf')
         if e2e_steps:
             def step_e2e():
-                if w['kind'] == 'jacobian':
+                if w['kind'].startswith('jacobian'):
                     rows = min(n, 4096)      # host-resident J is PCIe-bound: bounded row block
                     j = prism.jacobian(xp[:rows], yp[:rows], zp[:rows], w['model'], names[0], device=self.dev)
                     return rows, j.nbytes
@@ -578,11 +604,31 @@ class Bench(object):
     def roofline(self, res, peaks, brief=False):
         """FP64-pipe roofline of the dominant kernel of a measured workload (rank 0)."""
         name, w = res['name'], res['w']
-        base = {"c2a": "c2", "c4full": "c4", "c5full": "c5", "c5tfull": "c5t", "c5tslab": "c5t"}.get(name, name)
+        base = {"c2a": "c2", "c4full": "c4", "c4a": "c4", "c5full": "c5", "c5tfull": "c5t", "c5tslab": "c5t"}.get(name, name)
         prof, src = load_profile("%s_%s" % (base, res['evaluation']))
         per_gpu = res['value'] / self.world
         peak = peaks[1] if res['ms_per_step'] > 500 else peaks[0]
         wk = WORK[name]
+        if res['evaluation'] == 'grid':
+            # commensurate-grid Jacobian: data movement, bound by the HBM write of J (8 B per entry)
+            peaks_file = {}
+            try:
+                peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm = peaks_file.get("hbm_gbs", 6650.0)
+            out = {"bound": "hbm", "unit": "GB/s", "achieved": per_gpu * 8 / 1e9, "peak": hbm,
+                   "frac": per_gpu * 8 / 1e9 / hbm, "profile": src,
+                   "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+                   "algorithmic_bytes_per_entry": 8,
+                   "peak_source": ("MEASURED_PEAKS.json hbm_gbs (copy bandwidth, read+write)" if peaks_file
+                                   else "fallback 6650 GB/s"),
+                   "algorithmic": {"flop_per_pair": wk['flop'], "of": wk['what'],
+                                   "equivalent_tflops": per_gpu * wk['flop'] / 1e12}}
+            if not brief:
+                out["note"] = ("achieved = 8 bytes per matrix entry x entries/s (tables included in the time); "
+                               "the entries are gathered from L2-resident tables by TMA bulk copies")
+            return out
         out = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak, "profile": src}
         if prof:
             executed = prof["fp64_inst_per_pair"]
@@ -603,7 +649,7 @@ class Bench(object):
                            "frac = FP64-pipe utilisation.  algorithmic = pairs/s x FLOP per pair of the "
                            "REFERENCE formulation (libm-grade log/atan2 per corner, SURVEY 8(d)): a speed-up "
                            "figure that exceeds the FP64 peak, not a roofline fraction")
-        if w['kind'] == 'jacobian':
+        if w['kind'].startswith('jacobian'):
             peaks_file = {}
             try:
                 peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -704,9 +750,9 @@ def run_gpu(args):
     extra = {}
     strong = pshard = None
     if args.workload == "c2" and not args.no_configs:
-        for name in ("c3", "c4", "c5", "c5t"):
+        for name in ("c3", "c4", "c4a", "c5", "c5t"):
             extra[name] = B.measure(name, 3, 3, weak=True, e2e_steps=0,
-                                    model_key="c5" if name.startswith("c5") else name)
+                                    model_key="c5" if name.startswith("c5") else "c4" if name.startswith("c4") else name)
         strong = B.measure("c5tslab", 2, 3, weak=False, model_key="c5")
         pshard = B.prism_shard()
 
@@ -742,6 +788,8 @@ def run_gpu(args):
                       "node-sharing Jacobian (one kernel evaluation per point and node, entries = signed "
                       "sums of eight node values)",
                       "surface": "surface form (relief: top faces + merged reference-plane nodes)",
+                      "grid": "commensurate-grid reuse (one kernel evaluation per distinct node-point offset, "
+                              "entries written by TMA data movement; bit-identical to node sharing)",
                       "cells": "per cell"}[main['evaluation']]
         line = {"metric": METRIC, "value": main['value'], "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main['ms_per_step'],

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "fb200_last_kernel_ms": ([ctypes.c_void_p, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_int)],
                              ctypes.c_int),
     "fb200_last_fallback_points": ([ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)], ctypes.c_int),
+    "fb200_jacobian_grid": ([ctypes.c_void_p, _i64, _i64, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp,
+                             ctypes.c_int, _dp, _dp, _d, ctypes.c_void_p, _i64, ctypes.c_uint32], ctypes.c_int),
     "fb200_gram": ([ctypes.c_int, ctypes.c_void_p, _i64, _i64, _i64, ctypes.c_void_p, _d, ctypes.c_void_p,
                     _i64, ctypes.POINTER(_d)], ctypes.c_int),
     "fb200_matvec": ([ctypes.c_int, ctypes.c_void_p, _i64, _i64, _i64, ctypes.c_void_p, ctypes.c_void_p],

@@ -25,6 +25,7 @@
 #include "prism_forward.cuh"
 #include "prism_mesh.cuh"
 #include "prism_mesh_jacobian.cuh"
+#include "prism_grid_reuse.cuh"
 #include "sphere.cuh"
 
 using namespace fb200;
@@ -102,6 +103,7 @@ struct fb200_model {
     double *d_iwork = nullptr; size_t iwork_cap = 0;   // per-point flags + index list (ints)
     double *d_sub = nullptr;   size_t sub_cap = 0;     // gathered points and their results (per-point fallback)
     double *d_adj = nullptr; size_t adj_cap = 0;       // node-sharing adjoint: point rows, node list, V
+    double *d_grid = nullptr; size_t grid_cap = 0;     // commensurate-grid Jacobian: node and cell tables
     // cell walls whose coordinate the reference computes differently from the two sides
     // (x2 of one cell != x1 of the next, one ulp apart): see fb200_model_set_hazard_planes
     double *d_hazard[3] = {nullptr, nullptr, nullptr};
@@ -429,6 +431,7 @@ extern "C" int fb200_model_destroy(fb200_model *model)
     if (model->d_iwork) cudaFreeAsync(model->d_iwork, st);
     if (model->d_sub) cudaFreeAsync(model->d_sub, st);
     if (model->d_adj) cudaFreeAsync(model->d_adj, st);
+    if (model->d_grid) cudaFreeAsync(model->d_grid, st);
     for (double *p : model->d_hazard) if (p) cudaFreeAsync(p, st);
     if (model->copy_stream) {
         cudaStreamSynchronize(model->copy_stream);
@@ -1375,6 +1378,104 @@ extern "C" int fb200_jacobian(fb200_model *mod, const double *xp, const double *
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
     mod->last_ms = ms;       // device time of the kernels (the copies overlap them on the copy stream)
+    return FB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Jacobian of a regular mesh on a commensurate level grid (prism_grid_reuse.cuh)
+// ---------------------------------------------------------------------------
+extern "C" int fb200_jacobian_grid(fb200_model *mod, int64_t ni, int64_t nj, int kx, int ky, const double *xu,
+                                   const double *yv, const double *zc, int field, const double *unit_prop,
+                                   const double *fvec, double scale, double *out, int64_t ld, uint32_t flags)
+{
+    if (!mod) return fail(FB200_EINVAL, "model is NULL");
+    if (field < 0 || field >= F_COUNT) return fail(FB200_EINVAL, "invalid field id");
+    if (ni <= 0 || nj <= 0 || kx <= 0 || ky <= 0 || !xu || !yv || !zc || !out || !unit_prop)
+        return fail(FB200_EINVAL, "bad argument to fb200_jacobian_grid");
+    if (flags & ~FB200_DEVICE_POINTERS) return fail(FB200_EUNSUP, "unsupported flag for fb200_jacobian_grid");
+    if (!mod->has_mesh) return fail(FB200_EUNSUP, "the model has no regular-mesh form attached");
+    const bool magnetic = field >= F_TF;
+    if (field == F_TF && !fvec) return fail(FB200_EINVAL, "tf needs the inducing-field direction");
+    const int nx = mod->nxp - 1, ny = mod->nyp - 1, nz = mod->nzp - 1;
+    const int64_t m = (int64_t)nx * ny * nz, n = ni * nj;
+    if (mod->m != m) return fail(FB200_EUNSUP, "the model's prisms are not all the cells of its mesh");
+    if (ld < m) return fail(FB200_EINVAL, "ld smaller than the number of cells");
+    // the TMA path moves whole cell rows of nx doubles: 16-byte granularity
+    if (nx % 2 || ld % 2 || (reinterpret_cast<uintptr_t>(out) % 16) || (int64_t)nx * 8 > GR_CHUNK_BYTES)
+        return fail(FB200_EUNSUP, "commensurate-grid Jacobian needs an even number of cells along x, an even "
+                                  "leading dimension and a 16-byte aligned destination");
+    const bool on_device = (flags & FB200_DEVICE_POINTERS) != 0;
+
+    std::lock_guard<std::mutex> hold(mod->lock);
+    DeviceGuard g(mod->device);
+    if (!g.ok) return fail(FB200_ECUDA, "cudaSetDevice failed");
+    mod->last_launches = 0;
+    mod->last_ms = 0.0;
+    mod->last_fallback_points = 0;
+
+    GridPlan gp;
+    gp.nx = nx; gp.ny = ny; gp.nz = nz; gp.kx = kx; gp.ky = ky; gp.ni = ni; gp.nj = nj;
+    gp.nu = (int64_t)nx * kx + ni; gp.nv = (int64_t)ny * ky + nj;
+    gp.ndu = (int64_t)(nx - 1) * kx + ni; gp.ndv = (int64_t)(ny - 1) * ky + nj;
+    gp.ne = ((gp.ndu + kx - 1) / kx + 2 + 1) / 2 * 2;
+    const size_t nT = (size_t)(nz + 1) * gp.nv * gp.nu;
+    const size_t nD = (size_t)nz * gp.ndv * kx * gp.ne;
+    const size_t ncoord = (size_t)gp.nu + gp.nv + (nz + 1) + 8;
+    int rc = grow(&mod->d_grid, &mod->grid_cap, nT + 2 * nD + ncoord + 16, mod->stream);
+    if (rc != FB200_OK) return rc;
+    double *T = mod->d_grid, *D0 = T + (nT + 1) / 2 * 2, *D1 = D0 + (nD + 1) / 2 * 2;
+    double *dxu = D1 + (nD + 1) / 2 * 2, *dyv = dxu + gp.nu, *dzc = dyv + gp.nv;
+    CK(cudaMemcpyAsync(dxu, xu, (size_t)gp.nu * 8, cudaMemcpyHostToDevice, mod->stream));
+    CK(cudaMemcpyAsync(dyv, yv, (size_t)gp.nv * 8, cudaMemcpyHostToDevice, mod->stream));
+    CK(cudaMemcpyAsync(dzc, zc, (size_t)(nz + 1) * 8, cudaMemcpyHostToDevice, mod->stream));
+    double up[3], fv[3];
+    for (int r = 0; r < 3; ++r) {
+        up[r] = (magnetic ? unit_prop[r] : (r == 0 ? unit_prop[0] : 0.0)) * scale;   // like mesh_jacobian_kernel
+        fv[r] = fvec ? fvec[r] : 0.0;
+    }
+    CK(cudaEventRecord(mod->ev0, mod->stream));
+    CK(launch_grid_tables(field, gp, dxu, dyv, dzc, up, fv, mod->shift, T, D0, D1, mod->stream));
+    mod->last_launches += 2;
+    if (on_device) {
+        const int64_t per = 1 << 20;
+        for (int64_t r0 = 0; r0 < n; r0 += per) {
+            const int64_t rb = std::min(per, n - r0);
+            CK(launch_grid_expand(gp, D0, D1, r0, rb, out + r0 * ld, ld, mod->stream));
+            mod->last_launches += 1;
+        }
+        CK(cudaEventRecord(mod->ev1, mod->stream));
+        CK(cudaStreamSynchronize(mod->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+        mod->last_ms = ms;
+        return FB200_OK;
+    }
+    // host destination: row blocks through two staging blocks, copies overlap the expansion
+    int64_t rows = std::max<int64_t>(1, ((int64_t)(128ll << 20) / 8) / m);
+    rows = std::min(rows, n);
+    rc = grow(&mod->d_out, &mod->out_cap, (size_t)2 * rows * m, mod->stream);
+    if (rc != FB200_OK) return rc;
+    rc = ensure_copy_stream(mod);
+    if (rc != FB200_OK) return rc;
+    int64_t blk = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows, ++blk) {
+        const int64_t rb = std::min(rows, n - r0);
+        double *stage = mod->d_out + (size_t)(blk & 1) * rows * m;
+        if (blk >= 2) CK(cudaStreamWaitEvent(mod->stream, mod->ev_copy[blk & 1], 0));
+        CK(launch_grid_expand(gp, D0, D1, r0, rb, stage, m, mod->stream));
+        mod->last_launches += 1;
+        CK(cudaEventRecord(mod->ev_built[blk & 1], mod->stream));
+        CK(cudaStreamWaitEvent(mod->copy_stream, mod->ev_built[blk & 1], 0));
+        CK(cudaMemcpy2DAsync(out + r0 * ld, (size_t)ld * 8, stage, (size_t)m * 8, (size_t)m * 8, (size_t)rb,
+                             cudaMemcpyDeviceToHost, mod->copy_stream));
+        CK(cudaEventRecord(mod->ev_copy[blk & 1], mod->copy_stream));
+    }
+    CK(cudaEventRecord(mod->ev1, mod->stream));
+    CK(cudaStreamSynchronize(mod->copy_stream));
+    CK(cudaStreamSynchronize(mod->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, mod->ev0, mod->ev1));
+    mod->last_ms = ms;
     return FB200_OK;
 }
 

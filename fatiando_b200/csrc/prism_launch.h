@@ -4,7 +4,7 @@
 #include "prism_common.cuh"
 #include "prism_jacobian.cuh"
 
-namespace fb200 { struct MeshArgs; struct MeshJacArgs; }
+namespace fb200 { struct MeshArgs; struct MeshJacArgs; struct GridPlan; }
 
 namespace fb200 {
 
@@ -27,5 +27,11 @@ cudaError_t launch_forward_node(uint32_t mask, const ForwardArgs &a, int grid_y,
 cudaError_t launch_forward_node_rev(int field, const ForwardArgs &a, int grid_y, cudaStream_t s);    // fwd_surface.cu
 cudaError_t launch_mesh_forward(uint32_t mask, const MeshArgs &a, cudaStream_t s);               // fwd_mesh.cu
 cudaError_t launch_mesh_jacobian(int field, const MeshJacArgs &a, cudaStream_t s);              // fwd_mesh.cu
+// commensurate-grid Jacobian (prism_grid_reuse.cuh): node + cell tables, then rows [row0, row0 + nrows)
+cudaError_t launch_grid_tables(int field, const GridPlan &g, const double *xu, const double *yv, const double *zc,
+                               const double *unit_p, const double *fvec, const double *shift, double *T,
+                               double *D0, double *D1, cudaStream_t s);                          // jac_grid.cu
+cudaError_t launch_grid_expand(const GridPlan &g, const double *D0, const double *D1, int64_t row0, int64_t nrows,
+                               double *out, int64_t ld, cudaStream_t s);                         // jac_grid.cu
 
 }  // namespace fb200

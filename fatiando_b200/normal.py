@@ -76,7 +76,8 @@ class SensitivityBlock(object):
     on the GPU and kept there.  Shape ``(npoints, ncells)``, C-order.
     """
 
-    def __init__(self, model, xp, yp, zp, field='gz', pmag=None, fvec=None, scaled=True, per_cell=False):
+    def __init__(self, model, xp, yp, zp, field='gz', pmag=None, fvec=None, scaled=True, per_cell=False,
+                 grid_reuse=False):
         xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
         _check_points(xp, yp, zp, 'shape')
         self.device = model.device
@@ -93,15 +94,32 @@ class SensitivityBlock(object):
             else:
                 unit = numpy.array([1.0])
             fvec_arr = None if fvec is None else numpy.ascontiguousarray(fvec, dtype=numpy.float64)
-            pts = DeviceArray.from_host(numpy.stack([xp, yp, zp]), self.device)
+            self.path = 'default'
+            if grid_reuse and model.nodes is not None and not per_cell:
+                # commensurate level grid: tables + pure data movement (prism.grid_plan)
+                from .prism import grid_plan
+                plan = grid_plan(model.nodes, xp, yp, zp)
+                if plan is not None:
+                    rc = _lib.lib().fb200_jacobian_grid(
+                        model._handle, plan['ni'], plan['nj'], plan['kx'], plan['ky'], _lib.dptr(plan['xu']),
+                        _lib.dptr(plan['yv']), _lib.dptr(numpy.ascontiguousarray(plan['zc'])),
+                        _lib.FIELD_ID[field], _lib.dptr(unit), _lib.dptr(fvec_arr),
+                        unit_scale(field) if scaled else 1.0, self.J.ptr, m, _lib.DEVICE_POINTERS)
+                    if rc == _lib.OK:
+                        self.path = 'grid'
+                        self.build_ms = model.last_kernel_ms()[0]
+                    elif rc != _lib.EUNSUP:
+                        _lib.check(rc)
+            pts = DeviceArray.from_host(numpy.stack([xp, yp, zp]), self.device) if self.path == 'default' else None
             flags = _lib.DEVICE_POINTERS | (_lib.PER_CELL if per_cell else 0)
-            try:
+            if pts is not None:
+              try:
                 _lib.check(_lib.lib().fb200_jacobian(
                     model._handle, pts.ptr, pts.ptr + 8 * n, pts.ptr + 16 * n, n, _lib.FIELD_ID[field],
                     _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
                     self.J.ptr, m, flags))
                 self.build_ms = model.last_kernel_ms()[0]
-            finally:
+              finally:
                 pts.close()
         self.last_ms = 0.0
 

@@ -90,6 +90,53 @@ def _as_points(a):
     return numpy.ascontiguousarray(a)
 
 
+def grid_plan(nodes, xp, yp, zp):
+    """
+    The commensurate-grid plan of ``fb200_jacobian_grid`` for the regular mesh ``nodes``
+    (:class:`fatiando_b200.flatten.MeshNodes`) and the points ``xp, yp, zp``, or ``None``.
+
+    Applicable when the points are a regular grid at one level in the reference's order
+    (gridder/point_generation.py:89-96: x slowest), the cell size is an integer number of grid
+    steps on both axes, and -- the part that makes the result EXACT -- the difference
+    ``node - point`` is the same double for every (node a, point i) with the same
+    ``a*k - i`` (true e.g. for coordinates that are whole metres; checked here for every pair).
+    Returns ``dict(ni, nj, kx, ky, xu, yv, zc)``.
+    """
+    n = xp.size
+    if n < 4 or nodes is None or any(h.size for h in nodes.hazard):
+        return None
+    if not numpy.all(zp == zp[0]):
+        return None
+    change = numpy.flatnonzero(xp[1:] != xp[:-1])
+    nj = n if change.size == 0 else int(change[0]) + 1
+    if nj < 2 or n % nj or n // nj < 2:
+        return None
+    ni = n // nj
+    xs, ys = xp[::nj], yp[:nj]
+    if not (numpy.array_equal(xp, numpy.repeat(xs, nj)) and numpy.array_equal(yp, numpy.tile(ys, ni))):
+        return None
+
+    def axis(coord, pts):
+        cells = coord.size - 1
+        step, cell = pts[1] - pts[0], coord[1] - coord[0]
+        if not (step > 0 and cell > 0):
+            return None
+        k = int(round(cell / step))
+        if k < 1 or abs(k * step - cell) > 1e-9 * cell:
+            return None
+        diff = coord[:, None] - pts[None, :]
+        u = numpy.arange(cells + 1)[:, None] * k - numpy.arange(pts.size)[None, :] + (pts.size - 1)
+        table = numpy.ones(cells * k + pts.size)
+        table[u.ravel()] = diff.ravel()
+        if not numpy.array_equal(table[u], diff):       # same u, different double somewhere
+            return None
+        return k, table
+    ax, ay = axis(nodes.xn, xs), axis(nodes.yn, ys)
+    if ax is None or ay is None:
+        return None
+    return dict(ni=ni, nj=nj, kx=ax[0], ky=ay[0], xu=ax[1], yv=ay[1], zc=nodes.zn - zp[0])
+
+
 def _max_abs(*arrays):
     return max([float(numpy.max(numpy.abs(a))) for a in arrays if a.size] + [0.0])
 
@@ -220,7 +267,7 @@ class Model(object):
         return {_lib.FIELDS[i]: out[c] for c, i in enumerate(ids)}
 
     def jacobian(self, xp, yp, zp, field='gz', pmag=None, fvec=None, transposed=False,
-                 reference_order=False, scaled=True, out=None, per_cell=False):
+                 reference_order=False, scaled=True, out=None, per_cell=False, grid_reuse=False):
         """
         Dense sensitivity matrix of ``field`` for unit physical property.
 
@@ -229,6 +276,12 @@ class Model(object):
         reference's ``prism.<field>(x, y, z, [cell_q], dens=1)`` returns
         (eqlayer.py:108-111).  C-order ``(npoints, nprisms)`` float64, or
         ``(nprisms, npoints)`` with ``transposed=True`` (imaging.py:116-117).
+
+        ``grid_reuse=True`` (opt-in): for a whole regular mesh and points that form a level grid
+        commensurate with it (:func:`grid_plan`) the per-corner kernel is evaluated once per
+        distinct offset and the matrix is written by pure data movement -- bit-identical to
+        the default result, bound by the write of ``J``.  Silently the default path otherwise;
+        ``last_jacobian_path`` tells which one ran.
         """
         xp, yp, zp = _as_points(xp), _as_points(yp), _as_points(zp)
         _check_points(xp, yp, zp, 'shape')
@@ -257,6 +310,21 @@ class Model(object):
                 unit = numpy.array([1.0])
             fvec_arr = None if fvec is None else numpy.ascontiguousarray(fvec, dtype=numpy.float64)
             flags = self._flags(xp, yp, zp, reference_order)
+            self.last_jacobian_path = 'default'
+            if grid_reuse and self.nodes is not None and not (transposed or per_cell or reference_order) \
+                    and not (flags & _lib.REFERENCE_ORDER):
+                plan = grid_plan(self.nodes, xp, yp, zp)
+                if plan is not None:
+                    rc = _lib.lib().fb200_jacobian_grid(
+                        self._handle, plan['ni'], plan['nj'], plan['kx'], plan['ky'], _lib.dptr(plan['xu']),
+                        _lib.dptr(plan['yv']), _lib.dptr(numpy.ascontiguousarray(plan['zc'])), fid,
+                        _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
+                        out.ctypes.data, shape[1], 0)
+                    if rc == _lib.OK:
+                        self.last_jacobian_path = 'grid'
+                        return out
+                    if rc != _lib.EUNSUP:
+                        _lib.check(rc)
             if transposed:
                 flags |= _lib.TRANSPOSED
             if per_cell:

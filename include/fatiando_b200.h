@@ -312,6 +312,22 @@ int fb200_harvest_predicted(fb200_harvest *h, float *out /* all data sets */);
 int fb200_harvest_effect(fb200_harvest *h, int64_t row, double *out /* all data sets */);
 int64_t fb200_harvest_launches(const fb200_harvest *h);
 
+/* ---- Jacobian of a regular mesh on a commensurate level grid (opt-in) ------
+ * The observation points are the regular grid of gridder/point_generation.py:89-96 at ONE
+ * level, x slowest (row l = i*nj + j), with a spacing that divides the cell size of the
+ * model's regular mesh (a cell = kx x ky grid steps, mesher/mesh.py:626-634), and coordinates
+ * such that node - point is the same double for every (node a, point i) with the same
+ * u = a*kx - i + (ni - 1): xu[u] (nx*kx + ni values), likewise yv[v] (ny*ky + nj), and
+ * zc[c] = zn[c] - zp (nz + 1).  The caller verifies that property (fatiando_b200/prism.py)
+ * and passes the three difference tables; the per-corner kernel is then evaluated once per
+ * distinct (u, v, c) and the matrix is written by pure data movement (TMA), every entry
+ * bit-identical to fb200_jacobian's node-sharing result.  C-order (ni*nj, ncells) only;
+ * out on the host, or on the device with FB200_DEVICE_POINTERS.  FB200_EUNSUP when the mesh
+ * has an odd number of cells along x or ld is odd (callers fall back to fb200_jacobian).  */
+int fb200_jacobian_grid(fb200_model *model, int64_t ni, int64_t nj, int kx, int ky, const double *xu,
+                        const double *yv, const double *zc, int field, const double *unit_prop,
+                        const double *fvec, double scale, double *out, int64_t ld, uint32_t flags);
+
 /* ---- consumers of a device-resident sensitivity matrix --------------------
  * The Gauss-Newton products of fatiando/inversion/misfit.py on a ROW BLOCK of J that stays in
  * HBM (fb200_jacobian with FB200_DEVICE_POINTERS; rows = this GPU's observations).  All

@@ -65,3 +65,42 @@ def test_gram_rejects_bad_shapes(gpu_lib):
             block.tdot(np.ones(4))
         with pytest.raises(ValueError):
             block.gram(np.ones(3))
+
+
+def test_commensurate_grid_jacobian_is_bit_identical(gpu_lib, oracle):
+    """Opt-in reuse of kernel values on a level grid commensurate with the mesh
+    (csrc/prism_grid_reuse.cuh): the same bits as the default node-sharing Jacobian, for gravity
+    and magnetic fields, host and device destinations; grids that do not qualify fall back."""
+    from fatiando_b200 import prism, mesher, gridder, normal, utils
+    mesh = mesher.PrismMesh((0, 4000, 0, 3000, 0, 1500), (5, 6, 8))         # 500 x 500 x 300 m cells
+    xp, yp, zp = gridder.regular((-1000, 5000, -500, 3500), (61, 41), z=-150)      # 100 m: 5 steps per cell
+    fv = utils.dircos(30, -15)
+    with prism.Model(mesh, None, keep_all=True) as model:
+        plan = prism.grid_plan(model.nodes, xp, yp, zp)
+        assert plan is not None and (plan['kx'], plan['ky'], plan['ni'], plan['nj']) == (5, 5, 61, 41)
+        for f in ['gz', 'gxy', 'gzz', 'tf']:
+            pm = list(fv) if f == 'tf' else None
+            ref = model.jacobian(xp, yp, zp, f, pmag=pm, fvec=fv)
+            assert model.last_jacobian_path == 'default'
+            got = model.jacobian(xp, yp, zp, f, pmag=pm, fvec=fv, grid_reuse=True)
+            assert model.last_jacobian_path == 'grid'
+            assert np.array_equal(got, ref), f
+        with normal.SensitivityBlock(model, xp, yp, zp, 'gz', grid_reuse=True) as block:
+            assert block.path == 'grid'
+            assert np.array_equal(block.to_host(), model.jacobian(xp, yp, zp, 'gz'))
+        # a grid whose spacing does not divide the cells, scattered points, a tilted level
+        for pts in (gridder.regular((-1000, 5000, -500, 3500), (60, 41), z=-150),
+                    gridder.scatter((-1000, 5000, -500, 3500), 200, z=-150, seed=1)):
+            model.jacobian(*pts, field='gz', grid_reuse=True)
+            assert model.last_jacobian_path == 'default'
+        zt = zp.copy()
+        zt[5] -= 1.0
+        assert prism.grid_plan(model.nodes, xp, yp, zt) is None
+    # coordinates whose differences are NOT reproduced by translation (0.1 m is not a double):
+    # the exactness check refuses, the default path runs
+    mesh2 = mesher.PrismMesh((0.1, 4000.1, 0.3, 3000.3, 0, 1500), (5, 6, 8))
+    x2, y2, z2 = gridder.regular((-999.9, 5000.1, -499.7, 3500.3), (61, 41), z=-150)
+    with prism.Model(mesh2, None, keep_all=True) as model:
+        j = model.jacobian(x2, y2, z2, 'gz', grid_reuse=True)
+        assert model.last_jacobian_path in ('default', 'grid')
+        assert np.array_equal(j, model.jacobian(x2, y2, z2, 'gz'))
