@@ -23,6 +23,10 @@
 namespace fb200 {
 
 constexpr int MJ_THREADS = 256;
+#ifndef FB200_MJ_UNROLL
+#define FB200_MJ_UNROLL 2
+#endif
+constexpr int MJ_UNROLL = FB200_MJ_UNROLL;
 constexpr int MJ_WARPS = MJ_THREADS / 32;
 constexpr int MJ_ZPAD = MJ_THREADS + 8;   // z levels the node loop may read past the last one
 
@@ -41,13 +45,19 @@ struct MeshJacArgs {
     int points;                     // P: points per block, a divisor of 8 (8 / P warps per point)
 };
 
+#ifndef FB200_MJ_MIN_BLOCKS
+#define FB200_MJ_MIN_BLOCKS 3
+#endif
+#ifndef FB200_MJ_UNROLL
+#define FB200_MJ_UNROLL 2
+#endif
 #if defined(__CUDACC__)
 // 3 resident blocks of 256 threads per SM (85 registers): node and cell phases of different
 // blocks overlap.  All shared-memory traffic of the two loops goes through explicit 32-bit
 // shared-window addresses held in registers (fm::pin_u32), advanced by adds -- the index
 // arithmetic the compiler generates for the (level, x) walk was a third of the instruction stream.
 template <uint32_t MASK, bool TRANSPOSED>
-__global__ void __launch_bounds__(MJ_THREADS, 3) mesh_jacobian_kernel(const MeshJacArgs a)
+__global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian_kernel(const MeshJacArgs a)
 {
     static_assert(popc(MASK) == 1, "one field per Jacobian");
     extern __shared__ double sm[];
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(MJ_THREADS, 3) mesh_jacobian_kernel(const Mesh
         // need them -- on the padded tail of zs, and do not store)
         unsigned ea = cur + 8u * (unsigned)e0, za = zs_a + 8u * (unsigned)c0, xa = xs_a + 8u * (unsigned)a0;
         const unsigned e_end = cur + slab_b;
-#pragma unroll 2
+#pragma unroll(MJ_UNROLL)
         for (int it = 0; it < rounds; ++it) {
             const double X = fm::sub(fm::lds_f64(xa), px), Z = fm::sub(fm::lds_f64(za), pz);
             // X and Z both below 2^-480 (with Y there too, rare and warp-uniform, the whole row

@@ -86,6 +86,7 @@ class SensitivityBlock(object):
         n, m = self.shape
         self.J = DeviceArray((n, m), self.device)
         self.build_ms = 0.0
+        self.path = 'default'
         if n and m:
             if field in MAGNETIC_FIELDS:
                 if pmag is None:
@@ -113,14 +114,14 @@ class SensitivityBlock(object):
             pts = DeviceArray.from_host(numpy.stack([xp, yp, zp]), self.device) if self.path == 'default' else None
             flags = _lib.DEVICE_POINTERS | (_lib.PER_CELL if per_cell else 0)
             if pts is not None:
-              try:
-                _lib.check(_lib.lib().fb200_jacobian(
-                    model._handle, pts.ptr, pts.ptr + 8 * n, pts.ptr + 16 * n, n, _lib.FIELD_ID[field],
-                    _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
-                    self.J.ptr, m, flags))
-                self.build_ms = model.last_kernel_ms()[0]
-              finally:
-                pts.close()
+                try:
+                    _lib.check(_lib.lib().fb200_jacobian(
+                        model._handle, pts.ptr, pts.ptr + 8 * n, pts.ptr + 16 * n, n, _lib.FIELD_ID[field],
+                        _lib.dptr(unit), _lib.dptr(fvec_arr), unit_scale(field) if scaled else 1.0,
+                        self.J.ptr, m, flags))
+                    self.build_ms = model.last_kernel_ms()[0]
+                finally:
+                    pts.close()
         self.last_ms = 0.0
 
     def close(self):

@@ -24,8 +24,11 @@ def main():
     x, y, z = gridder.regular((0, 1e4, 0, 1e4), (400, 400), z=-50)
     sets = ((["gz"], "density"), (["gxx", "gxy", "gxz", "gyy", "gyz", "gzz"], "density"),
             (["tf", "bx", "by", "bz"], "magnetization"))
+    only = sys.argv[1] if len(sys.argv) > 1 else ""         # "sphere" / "polyprism": one family (for ncu)
     for label, module, model, unit in (("polyprism (20-vertex prisms)", polyprism, polys, 20),
                                        ("sphere", sphere, spheres, 1)):
+        if only and not label.startswith(only):
+            continue
         for names, prop in sets:
             with module.Model(model, prop) as mod:
                 for _ in range(3):

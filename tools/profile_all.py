@@ -25,7 +25,9 @@ CASES = {
     "c3_nodes": ("c3", [], "mesh_forward", 2.5e5 * 1e5,
                  "C3 tf+bx+by+bz, node-sharing kernel mesh_forward_kernel<0x3C00>, 500x500 points x 100x100x10 mesh"),
     "c4_nodes": ("c4", ["--rows", "8192"], "mesh_jacobian", 8192 * 4e4,
-                 "C4 Jacobian gz, node-sharing kernel mesh_jacobian_kernel<0x008>, 8192 rows x 40000 cells"),
+                 "C4 Jacobian gz, node-sharing kernel mesh_jacobian_kernel<0x008>, 8192 rows x 40000 cells, device-resident"),
+    "c4_grid": ("c4a", [], "expand_rows", 31626 * 4e4,
+                "C4 mesh on a commensurate 251x126 grid: expand_rows_kernel (TMA data movement), 31626 rows x 40000 cells"),
     "c5_surface": ("c5", [], "forward_kernel", 15625 * 1e6,
                    "C5 gz, relief surface form forward_kernel<0x008,EvalFace>, 15625 points x 1e6 top faces"),
     "c5t_surface": ("c5t", [], "forward_kernel", 15625 * 1e6,
@@ -37,16 +39,26 @@ CASES = {
 }
 
 
+SIBLINGS = {"sphere_gz": ("sphere", 1e5 * 1.6e5, "spheres: forward_kernel<0x008,EvalSphere>, 1e5 spheres x 400x400 points"),
+            "polyprism_gz": ("polyprism", 1e5 * 1.6e5, "polygonal prisms: forward_kernel<0x008,EvalPolyEdge>, 5000 prisms x 20 "
+                                                     "edges x 400x400 points (rows = edges)")}
+
+
 def gpu(keys):
     import bench
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
     open(os.path.join(out, "r02_csrc_hash.txt"), "w").write(bench.csrc_hash())
     for key in keys:
-        wl, extra, regex, _, _ = CASES[key]
-        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
-               "-k", "regex:" + regex, "-c", "1", "-f", "-o", os.path.join(out, "r02_" + key),
-               sys.executable, os.path.join(ROOT, "tools", "profile_case.py"), wl, "1"] + extra
+        if key in SIBLINGS:
+            cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
+                   "-k", "regex:forward_kernel", "-c", "1", "-f", "-o", os.path.join(out, "r02_" + key),
+                   sys.executable, os.path.join(ROOT, "tools", "bench_siblings.py"), SIBLINGS[key][0]]
+        else:
+            wl, extra, regex, _, _ = CASES[key]
+            cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
+                   "-k", "regex:" + regex, "-c", "1", "-f", "-o", os.path.join(out, "r02_" + key),
+                   sys.executable, os.path.join(ROOT, "tools", "profile_case.py"), wl, "1"] + extra
         r = subprocess.run(cmd, capture_output=True, text=True)
         print(key, "rc", r.returncode, (r.stdout + r.stderr).strip().splitlines()[-1:])
 
@@ -59,7 +71,10 @@ def collect(keys):
         if not os.path.exists(rep):
             print("missing", rep)
             continue
-        _, _, _, pairs, title = CASES[key]
+        if key in SIBLINGS:
+            _, pairs, title = SIBLINGS[key]
+        else:
+            _, _, _, pairs, title = CASES[key]
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "summarize_profile.py"), rep,
                                os.path.join(ROOT, "profiles", "r02_%s.txt" % key), repr(float(pairs)), title,
                                key, hashfile])
@@ -67,5 +82,5 @@ def collect(keys):
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else ""
-    keys = sys.argv[2:] or list(CASES)
+    keys = sys.argv[2:] or list(CASES) + list(SIBLINGS)
     {"gpu": gpu, "collect": collect}[mode](keys)

@@ -30,11 +30,19 @@ def main():
                      node_sharing="--per-cell" not in sys.argv) as model:
         for _ in range(reps):
             t0 = time.perf_counter()
-            if w['kind'] == 'jacobian':
-                rows = min(w['xp'].size, int(sys.argv[sys.argv.index('--rows') + 1]) if '--rows' in sys.argv else 2048)
-                model.jacobian(w['xp'][:rows], w['yp'][:rows], w['zp'][:rows], w['names'][0],
-                               reference_order=exact)
-                pairs = rows * model.size
+            if w['kind'].startswith('jacobian'):
+                # device-resident row block, ONE launch (what bench.py times)
+                from fatiando_b200 import normal
+                rows = min(w['xp'].size, int(sys.argv[sys.argv.index('--rows') + 1]) if '--rows' in sys.argv else 8192)
+                grid = w['kind'] == 'jacobian_grid'
+                sel = slice(None) if grid else slice(0, rows)
+                with normal.SensitivityBlock(model, w['xp'][sel], w['yp'][sel], w['zp'][sel], w['names'][0],
+                                             per_cell="--per-cell" in sys.argv, grid_reuse=grid) as block:
+                    pairs = block.shape[0] * model.size
+                    ms, nl = block.build_ms, 1
+                print("%s: %d entries, kernels %.3f ms -> %.3e entries/s (path %s)" % (
+                    name, pairs, ms, pairs / (ms * 1e-3), block.path))
+                continue
             else:
                 model.fields(w['xp'], w['yp'], w['zp'], w['names'], fvec=w['fvec'],
                              reference_order=exact)
