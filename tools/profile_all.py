@@ -22,16 +22,16 @@ sys.path.insert(0, ROOT)
 CASES = {
     "c2_nodes": ("c2", [], "mesh_forward", 4e4 * 5e4,
                  "C2 six tensor components, node-sharing kernel mesh_forward_kernel<0x3F0>, 200x200 points x 50x50x20 mesh"),
-    "c3_nodes": ("c3", [], "mesh_forward", 2.5e5 * 1e5,
-                 "C3 tf+bx+by+bz, node-sharing kernel mesh_forward_kernel<0x3C00>, 500x500 points x 100x100x10 mesh"),
+    "c3_nodes": ("c3", ["--points", "65536"], "mesh_forward", 65536 * 1e5,
+                 "C3 tf+bx+by+bz, node-sharing kernel mesh_forward_kernel<0x3C00>, 65536 of the 500x500 points x 100x100x10 mesh"),
     "c4_nodes": ("c4", ["--rows", "8192"], "mesh_jacobian", 8192 * 4e4,
                  "C4 Jacobian gz, node-sharing kernel mesh_jacobian_kernel<0x008>, 8192 rows x 40000 cells, device-resident"),
     "c4_grid": ("c4a", [], "expand_rows", 31626 * 4e4,
                 "C4 mesh on a commensurate 251x126 grid: expand_rows_kernel (TMA data movement), 31626 rows x 40000 cells"),
-    "c5_surface": ("c5", [], "forward_kernel", 15625 * 1e6,
-                   "C5 gz, relief surface form forward_kernel<0x008,EvalFace>, 15625 points x 1e6 top faces"),
-    "c5t_surface": ("c5t", [], "forward_kernel", 15625 * 1e6,
-                    "C5 gz+tensor, relief surface form forward_kernel<0x3F8,EvalFace>, 15625 points x 1e6 top faces"),
+    "c5_surface": ("c5", ["--points", "4096"], "forward_kernel", 4096 * 1e6,
+                   "C5 gz, relief surface form forward_kernel<0x008,EvalFace>, 4096 points x 1e6 top faces"),
+    "c5t_surface": ("c5t", ["--points", "4096"], "forward_kernel", 4096 * 1e6,
+                    "C5 gz+tensor, relief surface form forward_kernel<0x3F8,EvalFace>, 4096 points x 1e6 top faces"),
     "c2_cells": ("c2", ["--per-cell"], "forward_kernel", 4e4 * 5e4,
                  "C2 six tensor components, general per-cell kernel forward_kernel<0x3F0,EvalFast>"),
     "c1_cells": ("c1", [], "forward_kernel", 1e4 * 3,
@@ -44,40 +44,53 @@ SIBLINGS = {"sphere_gz": ("sphere", 1e5 * 1.6e5, "spheres: forward_kernel<0x008,
                                                      "edges x 400x400 points (rows = edges)")}
 
 
+def _title_pairs(key):
+    if key in SIBLINGS:
+        _, pairs, title = SIBLINGS[key]
+    else:
+        _, _, _, pairs, title = CASES[key]
+    return pairs, title
+
+
 def gpu(keys):
+    """Capture, summarise ON THE BOX (the reports are tens of MB each; gpurun brings back 64 MiB),
+    keep the text + JSON summaries under gpurun_out/."""
     import bench
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    open(os.path.join(out, "r02_csrc_hash.txt"), "w").write(bench.csrc_hash())
+    hashfile = os.path.join(out, "r02_csrc_hash.txt")
+    open(hashfile, "w").write(bench.csrc_hash())
     for key in keys:
+        rep = os.path.join(out, "r02_" + key)
         if key in SIBLINGS:
-            cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
-                   "-k", "regex:forward_kernel", "-c", "1", "-f", "-o", os.path.join(out, "r02_" + key),
-                   sys.executable, os.path.join(ROOT, "tools", "bench_siblings.py"), SIBLINGS[key][0]]
+            target = [os.path.join(ROOT, "tools", "bench_siblings.py"), SIBLINGS[key][0]]
+            regex = "forward_kernel"
         else:
             wl, extra, regex, _, _ = CASES[key]
-            cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
-                   "-k", "regex:" + regex, "-c", "1", "-f", "-o", os.path.join(out, "r02_" + key),
-                   sys.executable, os.path.join(ROOT, "tools", "profile_case.py"), wl, "1"] + extra
+            target = [os.path.join(ROOT, "tools", "profile_case.py"), wl, "1"] + extra
+        cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on",
+               "-k", "regex:" + regex, "-c", "1", "-f", "-o", rep, sys.executable] + target
         r = subprocess.run(cmd, capture_output=True, text=True)
-        print(key, "rc", r.returncode, (r.stdout + r.stderr).strip().splitlines()[-1:])
+        print(key, "rc", r.returncode, (r.stdout + r.stderr).strip().splitlines()[-1:], flush=True)
+        pairs, title = _title_pairs(key)
+        if os.path.exists(rep + ".ncu-rep"):
+            subprocess.call([sys.executable, os.path.join(ROOT, "tools", "summarize_profile.py"), rep + ".ncu-rep",
+                             os.path.join(out, "r02_%s.txt" % key), repr(float(pairs)), title, key, hashfile, out])
+            os.remove(rep + ".ncu-rep")
 
 
 def collect(keys):
+    """Copy the summaries that came back into profiles/ (tracked)."""
+    import shutil
     out = os.path.join(ROOT, "gpurun_out")
-    hashfile = os.path.join(out, "r02_csrc_hash.txt")
     for key in keys:
-        rep = os.path.join(out, "r02_%s.ncu-rep" % key)
-        if not os.path.exists(rep):
-            print("missing", rep)
-            continue
-        if key in SIBLINGS:
-            _, pairs, title = SIBLINGS[key]
-        else:
-            _, _, _, pairs, title = CASES[key]
-        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "summarize_profile.py"), rep,
-                               os.path.join(ROOT, "profiles", "r02_%s.txt" % key), repr(float(pairs)), title,
-                               key, hashfile])
+        for name in ("r02_%s.txt" % key, "r02_kernel_%s.json" % key):
+            src = os.path.join(out, name)
+            if os.path.exists(src):
+                shutil.copy(src, os.path.join(ROOT, "profiles", name))
+                print("profiles/" + name)
+            else:
+                print("missing", src)
 
 
 if __name__ == "__main__":

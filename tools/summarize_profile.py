@@ -34,7 +34,7 @@ KEYS = [
 ]
 
 
-def main(rep, out, pairs, title, key=None, hashfile=None):
+def main(rep, out, pairs, title, key=None, hashfile=None, jsondir=None):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -74,13 +74,13 @@ def main(rep, out, pairs, title, key=None, hashfile=None):
              "issue_active_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
              "dram_bytes_per_launch": (byts('dram__bytes_read.sum') or 0) + (byts('dram__bytes_write.sum') or 0),
              "registers": val('launch__registers_per_thread'),
-             "csrc_hash": h, "source": os.path.basename(rep),
+             "csrc_hash": h, "source": os.path.basename(rep) + " (summarised on the GPU box; the report itself is not kept)",
              "how": "ncu --set full --clock-control none --import-source on, one launch; instruction "
                     "counts from the source page (executed warp instructions x 32 / pairs)"}
-        path = os.path.join(root, 'profiles', 'r02_kernel_%s.json' % key)
+        path = os.path.join(jsondir or os.path.join(root, 'profiles'), 'r02_kernel_%s.json' % key)
         json.dump(d, open(path, 'w'), indent=1)
         print('wrote', path)
 
 
 if __name__ == '__main__':
-    main(*sys.argv[1:7])
+    main(*sys.argv[1:8])
