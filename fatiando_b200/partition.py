@@ -313,7 +313,7 @@ def adjoint_point_sharded(xp, yp, zp, prisms, data, field='gz', pmag=None, fvec=
 
 
 def gram_row_sharded(xp, yp, zp, prisms, field='gz', weights=None, residual=None, factor=1.0,
-                     pmag=None, fvec=None, device=None, to_host=True):
+                     pmag=None, fvec=None, device=None, to_host=True, evaluate=None):
     """
     The normal-equation pieces of a row-sharded sensitivity matrix (the Gauss-Newton step of
     ``fatiando.inversion``: ``Misfit.hessian`` = ``2 J^T W J``, misfit.py:250-256, and
@@ -326,6 +326,9 @@ def gram_row_sharded(xp, yp, zp, prisms, field='gz', weights=None, residual=None
 
     Returns ``(G, g, timings)``: numpy arrays (``to_host=True``) or CUDA tensors; ``g`` is None
     without a residual.  ``timings``: build / gram kernel / collective milliseconds, bytes.
+
+    ``evaluate(flat, x, y, z, field, weights, factor, residual) -> (G_local, g_local)`` replaces
+    the CUDA path (host arrays, any backend): the hook of the ``gloo`` tests.
     """
     import torch
     from .normal import SensitivityBlock
@@ -333,6 +336,18 @@ def gram_row_sharded(xp, yp, zp, prisms, field='gz', weights=None, residual=None
     rank, world = dist.get_rank(), dist.get_world_size()
     flat = prisms if isinstance(prisms, FlatModel) else flatten(prisms, None, override=True)
     sl = local_slice(xp.size, rank, world)
+    if evaluate is not None:
+        G_local, g_local = evaluate(flat, np.ascontiguousarray(xp[sl]), np.ascontiguousarray(yp[sl]),
+                                    np.ascontiguousarray(zp[sl]), field,
+                                    None if weights is None else np.ascontiguousarray(weights[sl]), factor,
+                                    None if residual is None else np.ascontiguousarray(residual[sl]))
+        G = torch.from_numpy(np.ascontiguousarray(G_local, dtype=np.float64))
+        dist.all_reduce(G, op=dist.ReduceOp.SUM)
+        g = None
+        if g_local is not None:
+            g = torch.from_numpy(np.ascontiguousarray(g_local, dtype=np.float64))
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return G.numpy(), None if g is None else g.numpy(), {}
     dev_index = default_device(rank) if device is None else device
     dev = torch.device('cuda', dev_index)
     w_local = None if weights is None else np.ascontiguousarray(weights[sl], dtype=np.float64)

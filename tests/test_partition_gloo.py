@@ -67,9 +67,16 @@ def _worker(rank, world, port, q):
         data = np.random.RandomState(5).normal(size=xp.size)
         rows, slj = partition.jacobian_row_sharded(xp, yp, zp, mesh, 'gz', evaluate=jac_eval)
         adj = partition.adjoint_point_sharded(xp, yp, zp, mesh, data, 'gz', evaluate=adj_eval)
+
+        def gram_eval(flat, x, y, z, field, w, factor, r):
+            J = jac_eval(flat, x, y, z, field)
+            return factor * (J.T @ (w[:, None] * J)), J.T @ (w * r)
+        wts = np.random.RandomState(6).uniform(0.5, 2.0, xp.size)
+        G, g, _ = partition.gram_row_sharded(xp, yp, zp, mesh, 'gz', weights=wts, residual=data, factor=2.0,
+                                             evaluate=gram_eval)
         q.put((rank, {k: v.copy() for k, v in obs.items()}, (sl.start, sl.stop),
                {k: v.copy() for k, v in mine.items()}, {k: v.copy() for k, v in pri.items()},
-               rows.copy(), (slj.start, slj.stop), adj.copy()))
+               rows.copy(), (slj.start, slj.stop), adj.copy(), G.copy(), g.copy()))
     finally:
         dist.destroy_process_group()
 
@@ -101,7 +108,12 @@ def test_sharding_world_size_2_gloo(oracle):
     flat_all = flatten(mesh, None, override=True)
     jac = oracle.jacobian('gz', xp, yp, zp, flat_all.bounds, [1.0])
     data = np.random.RandomState(5).normal(size=xp.size)
-    for rank, obs, (a, b), mine, pri, rows, (ja, jb), adj in results:
+    wts = np.random.RandomState(6).uniform(0.5, 2.0, xp.size)
+    for rank, obs, (a, b), mine, pri, rows, (ja, jb), adj, G, g in results:
+        # row-sharded normal equations: one all-reduce of the (m, m) matrix and of the gradient
+        np.testing.assert_allclose(G, 2.0 * (jac.T @ (wts[:, None] * jac)), rtol=1e-11,
+                                   atol=1e-14 * np.abs(jac).max() ** 2)
+        np.testing.assert_allclose(g, jac.T @ (wts * data), rtol=1e-11, atol=1e-14 * np.abs(jac).max())
         # row-sharded Jacobian: each rank holds exactly its rows; the adjoint's all-reduce
         # gives every rank the full J^T d
         assert np.array_equal(rows, jac[ja:jb]) and (ja, jb) == (a, b)
