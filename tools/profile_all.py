@@ -34,6 +34,14 @@ CASES = {
                     "C5 gz+tensor, relief surface form forward_kernel<0x3F8,EvalFace>, 4096 points x 1e6 top faces"),
     "c2_cells": ("c2", ["--per-cell"], "forward_kernel", 4e4 * 5e4,
                  "C2 six tensor components, general per-cell kernel forward_kernel<0x3F0,EvalFast>"),
+    "c2_cells_potential": ("c2", ["--per-cell", "--names", "potential"], "forward_kernel", 4e4 * 5e4,
+                           "potential alone, per-cell kernel forward_kernel<0x001,EvalFast> (168 registers, 3 blocks/SM), C2 model and grid"),
+    "c2_cells_gxyz": ("c2", ["--per-cell", "--names", "gx,gy,gz"], "forward_kernel", 4e4 * 5e4,
+                      "gx+gy+gz, per-cell kernel forward_kernel<0x00E,EvalFast> (3 blocks/SM), C2 model and grid"),
+    "c2_cells_all10": ("c2", ["--per-cell", "--names", "potential,gx,gy,gz,gxx,gxy,gxz,gyy,gyz,gzz"], "forward_kernel",
+                       4e4 * 5e4, "all ten gravity fields, per-cell kernel forward_kernel<0x3FF,EvalFast> (3 blocks/SM), C2 model and grid"),
+    "c3_cells": ("c3", ["--per-cell", "--points", "32768"], "forward_kernel", 32768 * 1e5,
+                 "C3 tf+bx+by+bz, per-cell kernel forward_kernel<0x3C00,EvalFast>, 32768 points x 1e5 prisms"),
     "c1_cells": ("c1", [], "forward_kernel", 1e4 * 3,
                  "C1 gz of 3 prisms x 100x100 points, per-cell kernel forward_kernel<0x008,EvalFast>"),
 }

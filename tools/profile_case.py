@@ -22,6 +22,8 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 3
     exact = "--exact" in sys.argv
     w = bench.make_workload(name, 1)
+    if "--names" in sys.argv:                    # another component set on the same model and points
+        w['names'] = sys.argv[sys.argv.index("--names") + 1].split(",")
     if "--points" in sys.argv:
         k = int(sys.argv[sys.argv.index("--points") + 1])
         for key in ("xp", "yp", "zp"):
