@@ -104,3 +104,17 @@ def test_commensurate_grid_jacobian_is_bit_identical(gpu_lib, oracle):
         j = model.jacobian(x2, y2, z2, 'gz', grid_reuse=True)
         assert model.last_jacobian_path in ('default', 'grid')
         assert np.array_equal(j, model.jacobian(x2, y2, z2, 'gz'))
+
+
+def test_commensurate_grid_jacobian_on_the_c4_mesh(gpu_lib):
+    """The multi-chunk TMA path (800 cell-row segments of 400 bytes per matrix row) on the C4 mesh:
+    bit-identical to the default node-sharing Jacobian, host destination."""
+    import bench
+    from fatiando_b200 import prism, gridder
+    w = bench.make_workload("c4", 1)
+    xp, yp, zp = gridder.regular((0, 10000, 0, 5000), (51, 26), z=-100)         # 200 m: one step per cell
+    with prism.Model(w['model'], None, keep_all=True) as model:
+        ref = model.jacobian(xp, yp, zp, 'gz')
+        got = model.jacobian(xp, yp, zp, 'gz', grid_reuse=True)
+        assert model.last_jacobian_path == 'grid'
+        assert got.shape == (51 * 26, 40000) and np.array_equal(got, ref)
