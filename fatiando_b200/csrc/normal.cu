@@ -11,16 +11,19 @@
 // collective moves real data (12.8 GB for the 40 000^2 matrix of config C4).
 //
 // The Gram matrix is a rank-n update: 2*n*m^2/2 FLOP on n*m*8 bytes -- at C4 (n = 31 250 per GPU,
-// m = 40 000) 1 250 FLOP per byte, FP64-pipe-bound.  gram_kernel is a register-tiled fp64 SYRK:
-// a 128 x 128 tile of G per block of 256 threads, 8 x 8 accumulators per thread, the two 16-row
+// m = 40 000) 1 250 FLOP per byte, FP64-pipe-bound.  gram_kernel is an fp64 SYRK on the FP64
+// tensor path (mma.sync m8n8k4): a 128 x 128 tile of G per block of 256 threads, a 64 x 32 warp
+// tile of 8 x 4 mma tiles (64 accumulator doubles per thread), the two 32-row
 // panels of J staged through a three-stage cp.async ring (8-byte copies, zero-filled past the
 // matrix edges, so any n, m and leading dimension work); only tiles on or above the diagonal are
-// computed, mirror_kernel fills the rest.  Per row of J a thread issues 64 DFMA per 8 16-byte
-// shared-memory loads (a warp's A loads are broadcasts, its B loads 256 contiguous bytes).
-// Measured: 70 % of the DFMA peak; 16 warps of 8 x 4 accumulators give the same (the limit is the
-// register-operand bandwidth of three-register DFMAs, 90 % in tools/fp64_pipe_probe.cu, times
-// the issue slots of the loads).
-// There is no fp64 tcgen05 path; the B200's FP64 rate is the DFMA rate.
+// computed, mirror_kernel fills the rest.  Per four rows of J a warp issues 32 DMMA (8192
+// multiply-adds) per 12 shared-memory loads; panel rows are padded by 8 doubles so that a
+// fragment load (4 rows x 8 consecutive doubles) takes the minimum of two wavefronts.
+// Round-2 history: the same tiling with DFMA register tiles (8 x 8 per thread) stopped at 72 % of
+// the DFMA peak -- three-register DFMAs cap at 90 % (tools/fp64_pipe_probe.cu) and the loads take
+// issue slots; tools/dmma_probe.cu shows the fp64 mma path running at the same 37 TFLOP/s with
+// one eighth of the instructions.  (tcgen05 has no fp64 operand type; mma.sync is the fp64
+// tensor path on sm_100a.)
 #include <algorithm>
 #include <cstdint>
 #include <string>
@@ -31,9 +34,15 @@
 namespace fb200 {
 
 constexpr int GT = 128;          // tile of G (rows and columns)
-constexpr int GK = 16;           // rows of J per stage
+#ifndef FB200_GK
+#define FB200_GK 32
+#endif
+#ifndef FB200_GSTAGES
+#define FB200_GSTAGES 3
+#endif
+constexpr int GK = FB200_GK;     // rows of J per stage
 constexpr int GTHREADS = 256;     // 8 warps, 8 x 8 accumulators per thread
-constexpr int GSTAGES = 3;
+constexpr int GSTAGES = FB200_GSTAGES;
 
 struct GramArgs {
     const double *J;
@@ -92,31 +101,42 @@ __device__ __forceinline__ void tile_of(int64_t id, int tiles, int *bi, int *bj)
     }
 }
 
+// fp64 tensor-core path: mma.sync m8n8k4 (DMMA).  tools/dmma_probe.cu measures 37.0 TFLOP/s for it
+// on B200 -- the same rate as the DFMA pipe, but one instruction carries 256 multiply-adds of a
+// warp instead of 32, so the issue slots that cap a DFMA SYRK at ~72 % are free.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+constexpr int GTP = GT + 8;      // padded panel row: 4 consecutive rows fall into 2 bank groups
+
 template <bool WEIGHTED, bool VEC>
 __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
 {
     extern __shared__ __align__(16) double smem[];
-    // stage s: A panel [GK][GT], B panel [GK][GT], weights [GK]
-    constexpr int STAGE = 2 * GK * GT + GK;
+    // stage s: A panel [GK][GTP], B panel [GK][GTP], weights [GK]
+    constexpr int STAGE = 2 * GK * GTP + GK;
     int bi, bj;
     tile_of((int64_t)blockIdx.x, a.tiles, &bi, &bj);
     const int64_t qa = (int64_t)bi * GT, qb = (int64_t)bj * GT;
-    const int tid = threadIdx.x;
-    // 16 row groups x 16 column groups; a warp = two row groups x 16 column groups, so that its
-    // A loads hit two addresses (broadcast) and its B loads 256 contiguous bytes
-    const int ty = tid >> 4, tx = tid & 15;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // 8 warps = 2 (rows) x 4 (columns); a warp owns 64 x 32 of the tile = 8 x 4 mma tiles
+    const int wr = (warp >> 2) * 64, wc = (warp & 3) * 32;
+    const int fr = lane >> 2, fk = lane & 3;          // fragment row / column index, k index
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
 
-    double acc[8][8];
+    double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int ktiles = (int)((a.n + GK - 1) / GK);
-    // Loader.  VEC: 16-byte copies, a thread owns the column pair c2 of rows r0, r0 + 4, ..
-    // (ld and m even, J 16-byte aligned); otherwise 8-byte copies, any layout.  Column validity
-    // is fixed per thread; row validity only matters in the last stage.
+    // Loader.  VEC: 16-byte copies, a thread owns the column pair c0 of rows r0, r0 + RSTEP, ..
+    // (ld even, J 16-byte aligned); otherwise 8-byte copies, any layout.  Column validity is
+    // fixed per thread; row validity only matters in the last stage.
     constexpr int PER = VEC ? (GK * GT / 2) / GTHREADS : (GK * GT) / GTHREADS;     // copies per panel
     constexpr int RSTEP = VEC ? GTHREADS / (GT / 2) : GTHREADS / GT;               // rows between copies
     const int r0 = VEC ? tid / (GT / 2) : tid / GT;
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
     const double *pa = a.J + (int64_t)r0 * a.ld + (a_bytes ? qa + c0 : 0);
     const double *pb = a.J + (int64_t)r0 * a.ld + (b_bytes ? qb + c0 : 0);
     const int64_t row_step = (int64_t)RSTEP * a.ld, stage_step = (int64_t)GK * a.ld;
-    const unsigned d0 = (unsigned)(r0 * GT + c0) * 8u;
+    const unsigned d0 = (unsigned)(r0 * GTP + c0) * 8u;
     auto issue = [&](int t) {
         const unsigned dst = sbase + (unsigned)((t % GSTAGES) * STAGE) * 8u + d0;
         const int64_t l0 = (int64_t)t * GK + r0;
@@ -135,9 +155,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
         if (VEC && full) {                      // the common case: no row predicates
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
-                const unsigned off = (unsigned)(i * RSTEP * GT) * 8u;
+                const unsigned off = (unsigned)(i * RSTEP * GTP) * 8u;
                 cp_async16(dst + off, ra, a_bytes);
-                cp_async16(dst + off + (unsigned)(GK * GT) * 8u, rb, b_bytes);
+                cp_async16(dst + off + (unsigned)(GK * GTP) * 8u, rb, b_bytes);
                 ra += row_step;
                 rb += row_step;
             }
@@ -145,20 +165,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const bool ok = full || l0 + i * RSTEP < a.n;
-            const unsigned off = (unsigned)(i * RSTEP * GT) * 8u;
+            const unsigned off = (unsigned)(i * RSTEP * GTP) * 8u;
             if (VEC) {
                 cp_async16(dst + off, ok ? ra : a.J, ok ? a_bytes : 0);
-                cp_async16(dst + off + (unsigned)(GK * GT) * 8u, ok ? rb : a.J, ok ? b_bytes : 0);
+                cp_async16(dst + off + (unsigned)(GK * GTP) * 8u, ok ? rb : a.J, ok ? b_bytes : 0);
             } else {
                 cp_async8(dst + off, ok ? ra : a.J, ok && a_bytes);
-                cp_async8(dst + off + (unsigned)(GK * GT) * 8u, ok ? rb : a.J, ok && b_bytes);
+                cp_async8(dst + off + (unsigned)(GK * GTP) * 8u, ok ? rb : a.J, ok && b_bytes);
             }
             ra += row_step;
             rb += row_step;
         }
         if (WEIGHTED && tid < GK) {
             const int64_t l = (int64_t)t * GK + tid;
-            cp_async8(sbase + (unsigned)((t % GSTAGES) * STAGE + 2 * GK * GT + tid) * 8u,
+            cp_async8(sbase + (unsigned)((t % GSTAGES) * STAGE + 2 * GK * GTP + tid) * 8u,
                       a.w + (l < a.n ? l : 0), l < a.n);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -175,38 +195,39 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_kernel(const GramArgs a)
         if (t + GSTAGES - 1 < ktiles) issue(t + GSTAGES - 1);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         const double *As = smem + (t % GSTAGES) * STAGE;
-        const double *Bs = As + GK * GT;
-        const double *Ws = Bs + GK * GT;
+        const double *Bs = As + GK * GTP;
+        const double *Ws = Bs + GK * GTP;
 #pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            double av[8], bv[8];
+        for (int k4 = 0; k4 < GK; k4 += 4) {
+            // A fragment of mma tile i: J[l = k4 + fk][qa + wr + 8 i + fr]; B likewise with the columns
+            double av[8], bv[4];
+            const double *ar = As + (k4 + fk) * GTP + wr + fr;
+            const double *br = Bs + (k4 + fk) * GTP + wc + fr;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double2 v = *reinterpret_cast<const double2 *>(As + k * GT + ty * 2 + 32 * i);
-                av[2 * i] = v.x; av[2 * i + 1] = v.y;
-                const double2 u = *reinterpret_cast<const double2 *>(Bs + k * GT + tx * 2 + 32 * i);
-                bv[2 * i] = u.x; bv[2 * i + 1] = u.y;
-            }
+            for (int i = 0; i < 8; ++i) av[i] = ar[8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = br[8 * j];
             if (WEIGHTED) {
-                const double wk = Ws[k];
+                const double wk = Ws[k4 + fk];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bv[j] *= wk;
+                for (int j = 0; j < 4; ++j) bv[j] *= wk;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], av[i], bv[j]);
         }
     }
-    // this thread's rows {ty*2 + 32 i + (0,1)} and columns {tx*2 + 32 j + (0,1)} of the tile
+    // accumulator fragment of mma tile (i, j): row 8 i + fr, columns 8 j + 2 fk + (0, 1)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int64_t row = qa + ty * 2 + 32 * (i >> 1) + (i & 1);
+        const int64_t row = qa + wr + 8 * i + fr;
         if (row >= a.m) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t col = qb + tx * 2 + 32 * (j >> 1) + (j & 1);
-            if (col < a.m) a.G[row * a.ldg + col] = acc[i][j] * a.factor;
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = qb + wc + 8 * j + 2 * fk;
+            if (col < a.m) a.G[row * a.ldg + col] = acc[i][j][0] * a.factor;
+            if (col + 1 < a.m) a.G[row * a.ldg + col + 1] = acc[i][j][1] * a.factor;
         }
     }
 }
@@ -283,7 +304,7 @@ extern "C" int fb200_gram(int device, const double *J, int64_t n, int64_t m, int
     a.tiles = (int)((m + GT - 1) / GT);
     const int64_t blocks = (int64_t)a.tiles * (a.tiles + 1) / 2;
     if (blocks > 2147483647ll) return set_error(FB200_EUNSUP, "matrix too large for one launch");
-    const size_t smem = (size_t)GSTAGES * (2 * GK * GT + GK) * sizeof(double);
+    const size_t smem = (size_t)GSTAGES * (2 * GK * GTP + GK) * sizeof(double);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms) {
         FB_CK(cudaEventCreate(&e0));
