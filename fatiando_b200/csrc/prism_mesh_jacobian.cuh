@@ -60,10 +60,11 @@ template <uint32_t MASK, bool TRANSPOSED>
 __global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian_kernel(const MeshJacArgs a)
 {
     static_assert(popc(MASK) == 1, "one field per Jacobian");
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int P = a.points;
     const int nxp = a.nxp, nzp = a.nzp, nx = nxp - 1, nz = nzp - 1, ny = a.nyp - 1;
-    const int slab = nzp * nxp;
+    const int stride = nxp + (nxp & 1);            // slab rows padded to an even length: 16-byte rows
+    const int slab = nzp * stride;
     const int64_t ld = a.ld;
     const double *const yn = a.yn;
     double *buf0 = sm, *buf1 = sm + (size_t)P * slab;
@@ -91,14 +92,18 @@ __global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian
     const unsigned xs_a = fm::pin_u32(smem_u32(xs)), zs_a = fm::pin_u32(smem_u32(zs));
     // (byte strides pinned too: derived from kernel parameters they would be re-formed from
     // uniform registers at every use)
-    const unsigned slab_b = fm::pin_u32(8u * (unsigned)slab), row_b = fm::pin_u32(8u * (unsigned)nxp);
-    const unsigned xs_end = xs_a + row_b;
+    const unsigned row_b = fm::pin_u32(8u * (unsigned)nxp), stride_b = fm::pin_u32(8u * (unsigned)stride);
+    const unsigned xs_end = xs_a + row_b, zs_end = zs_a + 8u * (unsigned)nzp;
+    const unsigned pad_b = stride_b - row_b;
+    // two adjacent entries go out as one 16-byte store when the matrix allows it
+    const bool vec_store = !TRANSPOSED && (nx % 2 == 0) && (ld % 2 == 0) &&
+                           (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
 
     const int step = 32 * nsub;
-    const int rounds = (slab + step - 1) / step;   // same trip count for every lane (warp votes inside)
+    const int rounds = (nzp * nxp + step - 1) / step;   // same trip count for every lane (warp votes inside)
     const int dq = step / nxp, dr = step - dq * nxp;        // one step in (level, x index) form
-    const unsigned step_b = fm::pin_u32(8u * (unsigned)step), dq_b = fm::pin_u32(8u * (unsigned)dq),
-                   dr_b = fm::pin_u32(8u * (unsigned)dr);
+    const unsigned dq_b = fm::pin_u32(8u * (unsigned)dq), dr_b = fm::pin_u32(8u * (unsigned)dr);
+    const unsigned step_b = fm::pin_u32(8u * (unsigned)(dq * stride + dr));     // one step in the padded slab
     unsigned cur = fm::pin_u32(smem_u32(buf0 + (size_t)p * slab)), prev = fm::pin_u32(smem_u32(buf1 + (size_t)p * slab));
     const int e0 = sub * 32 + lane;
     const int c0 = e0 / nxp, a0 = e0 - c0 * nxp;
@@ -109,8 +114,8 @@ __global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian
         // ---- one kernel evaluation per (point, node) of this row ----
         // (lanes past the end of the slab keep computing -- the warp votes inside node_prims
         // need them -- on the padded tail of zs, and do not store)
-        unsigned ea = cur + 8u * (unsigned)e0, za = zs_a + 8u * (unsigned)c0, xa = xs_a + 8u * (unsigned)a0;
-        const unsigned e_end = cur + slab_b;
+        unsigned ea = cur + 8u * (unsigned)(c0 * stride + a0), za = zs_a + 8u * (unsigned)c0,
+                 xa = xs_a + 8u * (unsigned)a0;
 #pragma unroll(MJ_UNROLL)
         for (int it = 0; it < rounds; ++it) {
             const double X = fm::sub(fm::lds_f64(xa), px), Z = fm::sub(fm::lds_f64(za), pz);
@@ -121,11 +126,11 @@ __global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian
             double acc[1] = {0.0};
             const NodePrims np = node_prims<MASK>(X, Y, Z, fm::add(fm::mul(X, X), YY), bad_coord, sh, tb);
             node_add<MASK>(acc, np, X, Y, Z, u0, u1, u2, f);
-            if (ea < e_end) fm::sts_f64(ea, acc[0]);
+            if (za < zs_end) fm::sts_f64(ea, acc[0]);
             ea += step_b;
             xa += dr_b;
             za += dq_b;
-            if (xa >= xs_end) { xa -= row_b; za += 8u; }
+            if (xa >= xs_end) { xa -= row_b; za += 8u; ea += pad_b; }
         }
         __syncthreads();
         // ---- the cells between node rows b-1 and b ----
@@ -133,21 +138,40 @@ __global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian
         // the four node columns around the cell at level k, entry(k) = d(k+1) - d(k);
         // corner (x2, y2, z2) carries +, every lower bound flips the sign (_prism.pyx:104)
         if (b >= 1 && active) {
+            // a lane takes TWO adjacent cell columns (i0, i0 + 1): three node values per row and
+            // level (one 16-byte + one 8-byte load) instead of two per cell, one 16-byte store
             const int j = b - 1;
             const int64_t kstride = (int64_t)ny * nx * (TRANSPOSED ? ld : 1);
-            for (int i = sub * 32 + lane; i < nx; i += step) {
-                unsigned ca = cur + 8u * (unsigned)i, pa = prev + 8u * (unsigned)i;
-                double *dst = TRANSPOSED ? row_base + ((int64_t)j * nx + i) * ld
-                                         : row_base + ((int64_t)j * nx + i);
-                double below = (fm::lds_f64_v8(ca) - fm::lds_f64_v(ca)) - (fm::lds_f64_v8(pa) - fm::lds_f64_v(pa));
-#pragma unroll 4
+            const int npairs = (nx + 1) >> 1;
+            for (int t = sub * 32 + lane; t < npairs; t += step) {
+                const int i0 = 2 * t;
+                const bool two = i0 + 1 < nx;
+                unsigned ca = cur + 16u * (unsigned)t, pa = prev + 16u * (unsigned)t;
+                double *dst = TRANSPOSED ? row_base + ((int64_t)j * nx + i0) * ld
+                                         : row_base + ((int64_t)j * nx + i0);
+                double2 c = fm::lds_f64x2_v(ca), p = fm::lds_f64x2_v(pa);
+                double c2 = fm::lds_f64_v16(ca), p2 = fm::lds_f64_v16(pa);
+                double below0 = (c.y - c.x) - (p.y - p.x), below1 = (c2 - c.y) - (p2 - p.y);
+#pragma unroll 2
                 for (int k = 0; k < nz; ++k) {
-                    ca += row_b;
-                    pa += row_b;
-                    const double above = (fm::lds_f64_v8(ca) - fm::lds_f64_v(ca)) - (fm::lds_f64_v8(pa) - fm::lds_f64_v(pa));
-                    __stcs(dst, above - below);
+                    ca += stride_b;
+                    pa += stride_b;
+                    c = fm::lds_f64x2_v(ca); p = fm::lds_f64x2_v(pa);
+                    c2 = fm::lds_f64_v16(ca); p2 = fm::lds_f64_v16(pa);
+                    const double above0 = (c.y - c.x) - (p.y - p.x), above1 = (c2 - c.y) - (p2 - p.y);
+                    const double e0v = above0 - below0, e1v = above1 - below1;
+                    if (TRANSPOSED) {
+                        __stcs(dst, e0v);
+                        if (two) __stcs(dst + ld, e1v);
+                    } else if (vec_store) {
+                        __stcs(reinterpret_cast<double2 *>(dst), make_double2(e0v, e1v));
+                    } else {
+                        __stcs(dst, e0v);
+                        if (two) __stcs(dst + 1, e1v);
+                    }
                     dst += kstride;
-                    below = above;
+                    below0 = above0;
+                    below1 = above1;
                 }
             }
         }
@@ -159,7 +183,7 @@ __global__ void __launch_bounds__(MJ_THREADS, FB200_MJ_MIN_BLOCKS) mesh_jacobian
 // shared memory the kernel needs for P points per block
 inline size_t mesh_jacobian_smem(int nxp, int nzp, int P)
 {
-    return ((size_t)2 * P * nxp * nzp + nxp + nzp + MJ_ZPAD) * sizeof(double);
+    return ((size_t)2 * P * (nxp + (nxp & 1)) * nzp + nxp + nzp + MJ_ZPAD + 2) * sizeof(double);
 }
 
 template <uint32_t MASK>
