@@ -7,6 +7,8 @@
 // kernel translation units.  No entry point has a CPU compute path: if CUDA
 // is unusable they fail with FB200_ECUDA.
 #include <cuda_runtime.h>
+#include <thrust/execution_policy.h>
+#include <thrust/sort.h>
 
 #include <algorithm>
 #include <cmath>
@@ -246,6 +248,18 @@ __global__ void gather_points_kernel(const double *xp, const double *yp, const d
     out[i] = xp[l]; out[k_pad + i] = yp[l]; out[2 * k_pad + i] = zp[l];
 }
 
+__global__ void gather_values_kernel(const double *v, const int *idx, int64_t k, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) out[i] = v[idx[i]];
+}
+
+__global__ void add_kernel(double *dst, const double *src, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 // out[c*ld_out + idx[i]] = sub[c*ld_sub + i]
 __global__ void scatter_fields_kernel(const double *sub, int64_t ld_sub, const int *idx, int64_t k,
                                       double *out, int64_t ld_out)
@@ -275,13 +289,14 @@ __global__ void scatter_rows_kernel(const double *sub, int64_t ld_sub, int trans
 __global__ void adjoint_rows_kernel(const double *xp, const double *yp, const double *zp,
                                     const double *data, int64_t n, int64_t n_pad, int nw, double u0,
                                     double u1, double u2, double shx, double shy, double shz,
-                                    double *rows)
+                                    double *rows, const int *skip)
 {
     const int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_pad) return;
     const bool in = l < n;
     const int64_t s = in ? l : n - 1;
-    const double d = in ? data[s] : 0.0;
+    // points handed to the per-cell kernels (hazard walls) carry no weight here
+    const double d = (in && !(skip && skip[s])) ? data[s] : 0.0;
     rows[l] = xp[s];             rows[n_pad + l] = shx;
     rows[2 * n_pad + l] = yp[s]; rows[3 * n_pad + l] = shy;
     rows[4 * n_pad + l] = zp[s]; rows[5 * n_pad + l] = shz;
@@ -1527,24 +1542,72 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         d_xp = mod->d_pts; d_yp = mod->d_pts + np; d_zp = mod->d_pts + 2 * np; d_w = mod->d_pts + 3 * np;
         d_out = mod->d_out;
     }
-    // whole regular mesh in mesh order: node sharing (EvalNodeRev), unless a point lies in a
-    // hazard wall (fb200_model_set_hazard_planes)
+    // whole regular mesh in mesh order: node sharing (EvalNodeRev); points lying in a hazard wall
+    // (fb200_model_set_hazard_planes) are taken out of that sum and added by the per-cell kernels
     bool by_nodes = n > 0 && mod->has_mesh && !exact && !(flags & FB200_PER_CELL) &&
                     m == (int64_t)(mod->nxp - 1) * (mod->nyp - 1) * (mod->nzp - 1);
+    int *d_pflag = nullptr, *d_idx = nullptr;
+    int n_flagged = 0;
+    mod->last_fallback_points = 0;
     if (by_nodes && (mod->n_hazard[0] || mod->n_hazard[1] || mod->n_hazard[2])) {
+        const int64_t n_pad = (n + 63) / 64 * 64;
+        int rc = grow(&mod->d_iwork, &mod->iwork_cap, (size_t)n_pad + 8, mod->stream);
+        if (rc != FB200_OK) return rc;
+        d_pflag = reinterpret_cast<int *>(mod->d_iwork);
+        d_idx = d_pflag + n_pad;
+        CK(cudaMemsetAsync(d_pflag, 0, (size_t)n * sizeof(int), mod->stream));
         CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
         const double *coord[3] = {d_xp, d_yp, d_zp};
         for (int ax = 0; ax < 3; ++ax) {
             if (!mod->n_hazard[ax]) continue;
             near_plane_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(
-                coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag);
+                coord[ax], n, mod->d_hazard[ax], mod->n_hazard[ax], mod->d_flag, d_pflag);
             CK(cudaGetLastError());
         }
-        int raised = 0;
-        CK(cudaMemcpyAsync(&raised, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
+        CK(cudaMemsetAsync(mod->d_flag, 0, sizeof(int), mod->stream));
+        compact_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, mod->stream>>>(d_pflag, n, d_idx, mod->d_flag);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&n_flagged, mod->d_flag, sizeof(int), cudaMemcpyDeviceToHost, mod->stream));
         CK(cudaStreamSynchronize(mod->stream));
-        if (raised) by_nodes = false;
+        mod->last_fallback_points = n_flagged;
+        // the adjoint SUMS over the flagged points: put the (atomically appended) list in point
+        // order, so that the result does not change from run to run
+        if (n_flagged > 1) thrust::sort(thrust::cuda::par.on(mod->stream), d_idx, d_idx + n_flagged);
     }
+    // J^T d of the points (dx, dy, dz, dw)[0 .. cnt) by the per-cell kernels into dst[0 .. m)
+    auto per_cell = [&](const double *dx, const double *dy, const double *dz, const double *dw, int64_t cnt,
+                        double *dst) -> int {
+        // split the points so that every SM has work even for small models
+        const int64_t blocks_x = (m + JAC_THREADS - 1) / JAC_THREADS;
+        const int64_t tiles = (cnt + JAC_TILE - 1) / JAC_TILE;
+        int64_t nsplit = std::min<int64_t>(
+            std::max<int64_t>(1, ((int64_t)mod->sm_count * 20 + blocks_x - 1) / blocks_x), tiles);
+        nsplit = std::min<int64_t>(nsplit, 65535);
+        const int64_t rows = ((tiles + nsplit - 1) / nsplit) * JAC_TILE;
+        nsplit = (cnt + rows - 1) / rows;
+        int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * mp, mod->stream);
+        if (rc != FB200_OK) return rc;
+        AdjointArgs a;
+        std::memset(&a, 0, sizeof(a));
+        view_of(mod, magnetic, &a.j.model);
+        for (int r = 0; r < 3; ++r) a.j.unit_p[r] = magnetic ? unit_prop[r] : (r == 0 ? unit_prop[0] : 0.0);
+        for (int r = 0; r < 3; ++r) a.j.fvec[r] = fvec ? fvec[r] : 0.0;
+        a.j.xp = dx; a.j.yp = dy; a.j.zp = dz; a.j.n = cnt;
+        a.weights = dw;
+        a.part = mod->d_part;
+        a.ld_p = mp;
+        a.rows_per_split = rows;
+        CK(exact ? launch_adjoint_exact(field, a, (int)nsplit, mod->stream)
+                 : launch_adjoint_fast(field, a, (int)nsplit, mod->stream));
+        ReduceArgs r;
+        std::memset(&r, 0, sizeof(r));
+        r.part = mod->d_part; r.out = dst; r.n = m; r.ld = mp; r.ld_out = mp;
+        r.nc = 1; r.nsplit = (int)nsplit; r.scale[0] = scale; r.out_row[0] = 0;
+        reduce_partials_kernel<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, mod->stream>>>(r);
+        CK(cudaGetLastError());
+        mod->last_launches += 2;
+        return FB200_OK;
+    };
     if (n == 0) {
         fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, mod->stream>>>(d_out, m, 0.0);
         CK(cudaGetLastError());
@@ -1560,7 +1623,8 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         CK(cudaEventRecord(mod->ev0, mod->stream));
         adjoint_rows_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, mod->stream>>>(
             d_xp, d_yp, d_zp, d_w, n, n_pad, nw, unit_prop[0], magnetic ? unit_prop[1] : 0.0,
-            magnetic ? unit_prop[2] : 0.0, mod->shift[0], mod->shift[1], mod->shift[2], rows);
+            magnetic ? unit_prop[2] : 0.0, mod->shift[0], mod->shift[1], mod->shift[2], rows,
+            n_flagged ? d_pflag : nullptr);
         CK(cudaGetLastError());
         expand_nodes_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, mod->stream>>>(
             mod->d_nodes, mod->d_nodes + mod->nxp, mod->d_nodes + mod->nxp + mod->nyp, mod->nxp,
@@ -1594,40 +1658,30 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         adjoint_cells_kernel<<<(unsigned)((m + 255) / 256), 256, 0, mod->stream>>>(
             V, mod->nxp - 1, mod->nyp - 1, mod->nzp - 1, scale, d_out);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(mod->ev1, mod->stream));
         mod->last_launches = 5;
-    } else {
-        // split the points so that every SM has work even for small models
-        const int64_t blocks_x = (m + JAC_THREADS - 1) / JAC_THREADS;
-        const int64_t tiles = (n + JAC_TILE - 1) / JAC_TILE;
-        int64_t nsplit = std::min<int64_t>(
-            std::max<int64_t>(1, ((int64_t)mod->sm_count * 20 + blocks_x - 1) / blocks_x), tiles);
-        nsplit = std::min<int64_t>(nsplit, 65535);
-        const int64_t rows = ((tiles + nsplit - 1) / nsplit) * JAC_TILE;
-        nsplit = (n + rows - 1) / rows;
-        int rc = grow(&mod->d_part, &mod->part_cap, (size_t)nsplit * mp, mod->stream);
-        if (rc != FB200_OK) return rc;
-        AdjointArgs a;
-        std::memset(&a, 0, sizeof(a));
-        view_of(mod, magnetic, &a.j.model);
-        for (int r = 0; r < 3; ++r) a.j.unit_p[r] = magnetic ? unit_prop[r] : (r == 0 ? unit_prop[0] : 0.0);
-        for (int r = 0; r < 3; ++r) a.j.fvec[r] = fvec ? fvec[r] : 0.0;
-        a.j.xp = d_xp; a.j.yp = d_yp; a.j.zp = d_zp; a.j.n = n;
-        a.weights = d_w;
-        a.part = mod->d_part;
-        a.ld_p = mp;
-        a.rows_per_split = rows;
-        CK(cudaEventRecord(mod->ev0, mod->stream));
-        CK(exact ? launch_adjoint_exact(field, a, (int)nsplit, mod->stream)
-                 : launch_adjoint_fast(field, a, (int)nsplit, mod->stream));
-        ReduceArgs r;
-        std::memset(&r, 0, sizeof(r));
-        r.part = mod->d_part; r.out = d_out; r.n = m; r.ld = mp; r.ld_out = mp;
-        r.nc = 1; r.nsplit = (int)nsplit; r.scale[0] = scale; r.out_row[0] = 0;
-        reduce_partials_kernel<<<dim3((unsigned)((m + 255) / 256), 1), 256, 0, mod->stream>>>(r);
-        CK(cudaGetLastError());
+        if (n_flagged > 0) {
+            // the flagged points, cell by cell, added to the node-sharing sum of the others
+            const int64_t k = n_flagged, k_pad = (k + 31) / 32 * 32;
+            rc = grow(&mod->d_sub, &mod->sub_cap, (size_t)4 * k_pad + (size_t)mp, mod->stream);
+            if (rc != FB200_OK) return rc;
+            double *sx = mod->d_sub, *sw = sx + 3 * k_pad, *tmp = sw + k_pad;
+            gather_points_kernel<<<(unsigned)((k + 255) / 256), 256, 0, mod->stream>>>(d_xp, d_yp, d_zp, d_idx, k,
+                                                                                      k_pad, sx);
+            CK(cudaGetLastError());
+            gather_values_kernel<<<(unsigned)((k + 255) / 256), 256, 0, mod->stream>>>(d_w, d_idx, k, sw);
+            CK(cudaGetLastError());
+            rc = per_cell(sx, sx + k_pad, sx + 2 * k_pad, sw, k, tmp);
+            if (rc != FB200_OK) return rc;
+            add_kernel<<<(unsigned)((m + 255) / 256), 256, 0, mod->stream>>>(d_out, tmp, m);
+            CK(cudaGetLastError());
+            mod->last_launches += 3;
+        }
         CK(cudaEventRecord(mod->ev1, mod->stream));
-        mod->last_launches = 2;
+    } else {
+        CK(cudaEventRecord(mod->ev0, mod->stream));
+        int rc = per_cell(d_xp, d_yp, d_zp, d_w, n, d_out);
+        if (rc != FB200_OK) return rc;
+        CK(cudaEventRecord(mod->ev1, mod->stream));
     }
     if (!on_device)
         CK(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, mod->stream));

@@ -445,10 +445,16 @@ def test_hazard_walls_send_merged_forms_to_the_per_cell_kernels(gpu_lib):
                 j2, jc = j2.T, jc.T
             assert np.array_equal(j2[7], jc[7])
             assert np.array_equal(j2[others], ja[others])
-        # several flagged points, on two axes' walls would be the same mechanism; the adjoint
-        # sums over the points and still falls back as a whole
-        assert np.array_equal(geo.adjoint(xp, yp2, zp, data, 'gz'),
-                              geo.adjoint(xp, yp2, zp, data, 'gz', per_cell=True))
+        # the adjoint sums over the points: the flagged point leaves the node-sharing sum (zero
+        # weight) and is added by the per-cell kernels
+        adj = geo.adjoint(xp, yp2, zp, data, 'gz')
+        assert geo.last_fallback_points() == 1
+        rest = geo.adjoint(xp[others].copy(), yp2[others].copy(), zp[others].copy(), data[others].copy(), 'gz')
+        assert geo.last_fallback_points() == 0
+        one = geo.adjoint(xp[7:8].copy(), yp2[7:8].copy(), zp[7:8].copy(), data[7:8].copy(), 'gz', per_cell=True)
+        assert np.array_equal(adj, rest + one)
+        cells = geo.adjoint(xp, yp2, zp, data, 'gz', per_cell=True)
+        np.testing.assert_allclose(adj, cells, rtol=1e-9, atol=1e-10 * np.abs(cells).max())
 
 
 def test_relief_surface_form_equals_per_cell_and_oracle(gpu_lib, oracle):
