@@ -56,12 +56,20 @@ class FlatModel(object):
         fast-path range guard)."""
         if self.size == 0:
             return 0.0, np.inf
-        big = max(float(np.max(np.abs(b))) for b in self.bounds)
-        edges = np.concatenate([np.abs(self.bounds[1] - self.bounds[0]),
-                                np.abs(self.bounds[3] - self.bounds[2]),
-                                np.abs(self.bounds[5] - self.bounds[4])])
-        edges = edges[edges > 0]
-        return big, (float(edges.min()) if edges.size else np.inf)
+        hint = getattr(self, 'extent_hint', None)
+        if hint is not None:            # set by the flattener where the geometry says it all
+            return hint
+        big = 0.0
+        for b in self.bounds:           # min / max reductions: no temporaries
+            big = max(big, -float(b.min()), float(b.max()))
+        small = np.inf
+        for lo, hi in ((0, 1), (2, 3), (4, 5)):
+            e = self.bounds[hi] - self.bounds[lo]
+            np.abs(e, out=e)
+            e = e[e > 0]
+            if e.size:
+                small = min(small, float(e.min()))
+        return big, small
 
 
 def _is_scalar_property(value):
@@ -379,7 +387,12 @@ def flatten(prisms, prop=None, override=False, fvec=None):
         surface = relief_surface(prisms, prop, bounds=bounds if index.size == total else None)
     elif index.size == total:
         nodes = mesh_geometry(prisms)          # Jacobian / override models: geometry only
-    return FlatModel(bounds, dens, mag, index, total, nodes, surface)
+    flat = FlatModel(bounds, dens, mag, index, total, nodes, surface)
+    if _is_prism_mesh(prisms) and index.size:
+        # a regular mesh: the range guard's inputs follow from its bounds and cell size
+        flat.extent_hint = (max(abs(float(v)) for v in prisms.bounds),
+                            min(abs(float(d)) for d in prisms.dims))
+    return flat
 
 
 def _expand_scalar_magnetization(values, fvec):
