@@ -1,3 +1,5 @@
+# Records of one N-GPU box (gpurun --gpus N -- bash tools/record_multi.sh N): default bench, the north-star
+# runs, the full C4 matrix, row-sharded normal equations, NCCL check -> gpurun_out/r02_*
 mkdir -p gpurun_out
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"

@@ -1,3 +1,5 @@
+# Records of one 1-GPU box (gpurun -- bash tools/record_n1.sh): default bench, reference arm, per-cell runs,
+# launch list, normal equations, fallback check, harvester, siblings, smoke -> gpurun_out/r02_*
 mkdir -p gpurun_out
 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_ref.json 2>> gpurun_out/r02_bench_n1.err
