@@ -440,14 +440,80 @@ def _in_estimate(index, props, estimate):
     return index in estimate and _shares_prop(props, estimate[index])
 
 
+class _Candidates(dict):
+    """
+    ``{cell index: Neighbor}`` of one seed, in insertion order like the reference's dicts,
+    that also keeps the effect rows and the distances of its values as numpy arrays in the
+    same order: ``_grow`` hands them to the device as they are instead of walking thousands of
+    Python objects per accretion.  ``pop`` / ``update`` / item assignment and deletion keep the
+    arrays in step.
+    """
+
+    def __init__(self, items=()):
+        dict.__init__(self)
+        self.cells = numpy.empty(0, dtype=numpy.int64)
+        self.rows = numpy.empty(0, dtype=numpy.int64)
+        self.distances = numpy.empty(0, dtype=numpy.float64)
+        self.update(items)
+
+    def __setitem__(self, key, value):
+        if key in self:
+            at = int(numpy.flatnonzero(self.cells == key)[0])
+            self.rows[at], self.distances[at] = value._row, value.distance
+        else:
+            self.cells = numpy.append(self.cells, key)
+            self.rows = numpy.append(self.rows, value._row)
+            self.distances = numpy.append(self.distances, value.distance)
+        dict.__setitem__(self, key, value)
+
+    def update(self, other=(), **kw):
+        items = list(dict(other, **kw).items())
+        fresh = [(k, v) for k, v in items if k not in self]
+        for k, v in items:
+            if k in self:
+                self[k] = v
+        if fresh:
+            self.cells = numpy.concatenate([self.cells, numpy.array([k for k, _ in fresh], dtype=numpy.int64)])
+            self.rows = numpy.concatenate([self.rows, numpy.array([v._row for _, v in fresh], dtype=numpy.int64)])
+            self.distances = numpy.concatenate([self.distances,
+                                                numpy.array([v.distance for _, v in fresh], dtype=numpy.float64)])
+            for k, v in fresh:
+                dict.__setitem__(self, k, v)
+
+    def __delitem__(self, key):
+        dict.__delitem__(self, key)
+        keep = self.cells != key
+        self.cells, self.rows, self.distances = self.cells[keep], self.rows[keep], self.distances[keep]
+
+    def pop(self, key, *default):
+        if key not in self:
+            return dict.pop(self, key, *default)
+        value = dict.__getitem__(self, key)
+        del self[key]
+        return value
+
+    def popitem(self):
+        key = next(reversed(self))
+        return key, self.pop(key)
+
+    def clear(self):
+        dict.clear(self)
+        self.cells, self.rows, self.distances = self.cells[:0], self.rows[:0], self.distances[:0]
+
+    def setdefault(self, key, default=None):
+        if key not in self:
+            self[key] = default
+        return dict.__getitem__(self, key)
+
+
 def _get_neighbors(cell, neighborhood, estimate, mesh, engine, restrict):
     """New candidates around ``cell`` (a seed or an accreted Neighbor), with effect rows."""
     indexes = [n for n in _neighbor_indexes(cell.i, mesh, restrict)
                if not _is_neighbor(n, cell.props, neighborhood)
                and not _in_estimate(n, cell.props, estimate)]
     rows = engine.effects([_CellBounds(mesh, i) for i in indexes], cell.props)
-    return dict((i, Neighbor(i, cell.props, cell.seed, _distance(i, cell.seed, mesh), engine, int(r)))
-                for i, r in zip(indexes, rows))
+    return _Candidates((i, Neighbor(i, cell.props, cell.seed, _distance(i, cell.seed, mesh), engine, int(r)))
+                       for i, r in zip(indexes, rows))
 
 
 def _totals(values):
@@ -465,18 +531,22 @@ def _grow(neighbors, engine, totalmisfit, mu, regularizer, threshold):
     """
     if not neighbors:
         return None, None, None, None
-    cands = list(neighbors.values())
-    misfit, shape = engine.evaluate(numpy.fromiter((c._row for c in cands), dtype=numpy.int64,
-                                                   count=len(cands)))
+    if isinstance(neighbors, _Candidates):
+        rows, distances, cells = neighbors.rows, neighbors.distances, neighbors.cells
+    else:                                   # a plain dict handed in by a caller
+        cands = list(neighbors.values())
+        rows = numpy.fromiter((c._row for c in cands), dtype=numpy.int64, count=len(cands))
+        distances = numpy.fromiter((c.distance for c in cands), dtype=numpy.float64, count=len(cands))
+        cells = numpy.fromiter(neighbors.keys(), dtype=numpy.int64, count=len(cands))
+    misfit, shape = engine.evaluate(rows)
     misfit, shape = _totals(misfit), _totals(shape)
     ok = (misfit < totalmisfit) & (numpy.abs(misfit - totalmisfit) / totalmisfit >= threshold)
     if not ok.any():
         return None, None, None, None
-    reg = regularizer + numpy.fromiter((c.distance for c in cands), dtype=numpy.float64,
-                                       count=len(cands))
+    reg = regularizer + distances
     goal = numpy.where(ok, shape + mu * reg, numpy.inf)
     best = int(numpy.argmin(goal))          # first occurrence of the minimum
-    return cands[best], float(goal[best]), float(misfit[best]), float(reg[best])
+    return neighbors[int(cells[best])], float(goal[best]), float(misfit[best]), float(reg[best])
 
 
 def fmt_estimate(estimate, size):
