@@ -23,8 +23,8 @@
 
 namespace fb200 {
 
-// log and atan2 of ordinary arguments by the fast-path primitives (prism_fastmath.cuh: one
-// division + polynomial each, ~1 ulp), the library's for everything else (zeros, denormals,
+// log and atan2 of ordinary arguments by the table-driven primitives (prism_fastmath.cuh:
+// log_tab without a division, atan_tab with one; 0.3 ulp rms), the library's for everything else (zeros, denormals,
 // infinities, NaN, negative log arguments) so that the reference's behaviour in degenerate
 // geometry -- which its `dummy` guards are there for -- is untouched.
 FB_HD bool pp_ordinary(double v)          // finite, normal, non-zero
@@ -35,14 +35,14 @@ FB_HD bool pp_ordinary(double v)          // finite, normal, non-zero
 
 FB_HD double pp_log(double x)
 {
-    if (x > 0.0 && pp_ordinary(x)) return fm::log_ratio(x, 1.0);
+    if (x > 0.0 && pp_ordinary(x)) return fm::log_tab(x);        // division-free, 10 FP64 instructions
     return log(x);
 }
 
 FB_HD double pp_atan2(double y, double x)
 {
     if (pp_ordinary(y) && pp_ordinary(x)) {
-        const double r = fm::atan_ratio(y, x);                 // atan(y/x) in [-pi/2, pi/2]
+        const double r = fm::atan_ratio_tab(y, x);             // atan(y/x) in [-pi/2, pi/2], table-reduced
         if (x > 0.0) return r;
         const double s = (y < 0.0) ? -1.0 : 1.0;               // x < 0: +-pi on top
         return fma(s, fm::konst(4), fma(s, fm::konst(5), r));
@@ -52,7 +52,7 @@ FB_HD double pp_atan2(double y, double x)
 
 struct EvalPolyEdge {
     static constexpr bool NEEDS_FLAG = false;
-    static constexpr bool USES_TABLES = false;
+    static constexpr bool USES_TABLES = true;      // log / atan tables of prism_fastmath.cuh
     template <uint32_t MASK>
     static FB_HD_M void pair(double (&acc)[popc(MASK)], double xp, double yp, double zp,
                            double vx1, double vx2, double vy1, double vy2, double z1, double z2,
