@@ -33,6 +33,7 @@ data-path collective); value = all pairs of all ranks / max-over-ranks device ti
 import argparse
 import glob
 import hashlib
+import re
 import json
 import os
 import subprocess
@@ -77,16 +78,64 @@ def csrc_hash():
     return h.hexdigest()[:16]
 
 
+# translation unit each profiled kernel is instantiated in (profiles/r02_kernel_<key>.json)
+KERNEL_TU = {
+    "c1_cells": "fwd_fast_grav.cu", "c2_cells": "fwd_fast_grav.cu", "c2_cells_all10": "fwd_fast_grav.cu",
+    "c2_cells_gxyz": "fwd_fast_grav.cu", "c2_cells_potential": "fwd_fast_grav.cu",
+    "c3_cells": "fwd_fast_mag.cu",
+    "c2_nodes": "fwd_mesh.cu", "c3_nodes": "fwd_mesh.cu", "c4_nodes": "fwd_mesh.cu",
+    "c4_grid": "jac_grid.cu",
+    "c5_surface": "fwd_surface.cu", "c5t_surface": "fwd_surface.cu",
+    "polyprism_gz": "fwd_polyprism_exact.cu", "sphere_gz": "fwd_sphere.cu",
+}
+# host side of every launch (grid sizing, prism split, dispatch): part of every kernel's hash
+LAUNCH_FILES = ("prism_abi.cu", "abi_internal.h")
+
+
+def kernel_sources(key, root=None):
+    """
+    The files the profiled kernel of `key` is built from: its translation unit, everything that
+    reaches it through #include "..." (transitively), the launch code and the public header.
+    """
+    csrc = os.path.join(root or ROOT, "fatiando_b200", "csrc")
+    seen, todo = [], [KERNEL_TU[key]]
+    while todo:
+        f = todo.pop()
+        if f in seen:
+            continue
+        seen.append(f)
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(os.path.join(csrc, f)).read(), re.M):
+            if "/" not in inc:
+                todo.append(inc)
+    files = [os.path.join(csrc, f) for f in sorted(set(seen) | set(LAUNCH_FILES))]
+    return files + sorted(glob.glob(os.path.join(root or ROOT, "include", "*.h")))
+
+
+def kernel_hash(key, root=None):
+    """Hash of kernel_sources(key): what a profile of that kernel is valid for."""
+    h = hashlib.sha256()
+    for f in kernel_sources(key, root):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def load_profile(key):
-    """profiles/r02_kernel_<key>.json (tools/summarize_profile.py --json), or None when missing/stale."""
+    """
+    profiles/r02_kernel_<key>.json (tools/summarize_profile.py), or None when missing/stale.
+    A profile is valid while the sources of ITS kernel (kernel_sources) are unchanged; a change
+    to another kernel's header (e.g. polyprism.cuh for the prism kernels) does not touch it.
+    """
     path = os.path.join(ROOT, "profiles", "r02_kernel_%s.json" % key)
     try:
         d = json.load(open(path))
     except (OSError, ValueError):
         return None, "no profiles/r02_kernel_%s.json" % key
-    if d.get("csrc_hash") != csrc_hash():
-        return None, "profiles/r02_kernel_%s.json is stale (measured on csrc %s, this build is %s)" % (
-            key, d.get("csrc_hash"), csrc_hash())
+    if key not in KERNEL_TU:
+        return None, "profiles/r02_kernel_%s.json: no translation unit registered for this key" % key
+    if d.get("kernel_hash") != kernel_hash(key):
+        return None, "profiles/r02_kernel_%s.json is stale (measured on kernel sources %s, this build is %s)" % (
+            key, d.get("kernel_hash"), kernel_hash(key))
     return d, os.path.relpath(path, ROOT)
 
 

@@ -4,8 +4,8 @@ One command per side for the profiles bench.py's roofline depends on.
 On the GPU box (under gpurun, one GPU):
     python tools/profile_all.py gpu [keys...]
         one `ncu --set full --clock-control none --import-source on` capture of the dominant
-        kernel of each workload -> gpurun_out/r02_<key>.ncu-rep, plus gpurun_out/r02_csrc_hash.txt
-        (the hash of the snapshot's csrc/, what the captures are valid for).
+        kernel of each workload -> gpurun_out/r02_<key>.ncu-rep, plus gpurun_out/r02_kernel_hashes.json
+        (per kernel, the hash of the snapshot's sources of that kernel: what its capture is valid for).
 
 Here, afterwards:
     python tools/profile_all.py collect [keys...]
@@ -66,8 +66,9 @@ def gpu(keys):
     import bench
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    hashfile = os.path.join(out, "r02_csrc_hash.txt")
-    open(hashfile, "w").write(bench.csrc_hash())
+    import json
+    hashfile = os.path.join(out, "r02_kernel_hashes.json")
+    json.dump({k: bench.kernel_hash(k) for k in bench.KERNEL_TU}, open(hashfile, "w"))
     for key in keys:
         rep = os.path.join(out, "r02_" + key)
         if key in SIBLINGS:

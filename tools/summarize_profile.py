@@ -5,8 +5,10 @@ Write the judged summary of an ncu report into profiles/ (text, committed).
 
 With KEY it also writes profiles/r02_kernel_KEY.json, the numbers bench.py's roofline reads
 (executed FP64-pipe instructions per pair, DRAM bytes per launch, ...) together with the hash
-of csrc/ the capture was taken on (HASHFILE = the hash the GPU box computed from its snapshot,
-default: this tree's); bench.py refuses the file when the hash differs from its build's.
+of the sources THAT KERNEL is built from (bench.kernel_sources: its translation unit, the
+headers it includes, the launch code, the public header; HASHFILE = JSON {key: hash} the GPU
+box computed from its snapshot, default: this tree's); bench.py refuses the file when the
+hash differs from its build's.
 """
 import json
 import os
@@ -66,7 +68,8 @@ def main(rep, out, pairs, title, key=None, hashfile=None, jsondir=None):
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         sys.path.insert(0, root)
         import bench
-        h = open(hashfile).read().strip() if hashfile else bench.csrc_hash()
+        # HASHFILE: JSON {key: kernel hash} written by the GPU box from its snapshot
+        h = json.load(open(hashfile))[key] if hashfile else bench.kernel_hash(key)
         d = {"key": key, "kernel": name, "pairs_per_launch": float(pairs),
              "inst_per_pair": float(m.group(1)), "fp64_inst_per_pair": float(m.group(2)),
              "time_ms": val('gpu__time_duration.sum'),
@@ -74,7 +77,9 @@ def main(rep, out, pairs, title, key=None, hashfile=None, jsondir=None):
              "issue_active_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
              "dram_bytes_per_launch": (byts('dram__bytes_read.sum') or 0) + (byts('dram__bytes_write.sum') or 0),
              "registers": val('launch__registers_per_thread'),
-             "csrc_hash": h, "source": os.path.basename(rep) + " (summarised on the GPU box; the report itself is not kept)",
+             "kernel_hash": h,
+             "kernel_sources": [os.path.basename(f) for f in bench.kernel_sources(key)],
+             "source": os.path.basename(rep) + " (summarised on the GPU box; the report itself is not kept)",
              "how": "ncu --set full --clock-control none --import-source on, one launch; instruction "
                     "counts from the source page (executed warp instructions x 32 / pairs)"}
         path = os.path.join(jsondir or os.path.join(root, 'profiles'), 'r02_kernel_%s.json' % key)
