@@ -33,6 +33,41 @@ FB_HD bool pp_ordinary(double v)          // finite, normal, non-zero
     return e - 0x00100000u < 0x7fe00000u;
 }
 
+// Roots and quotients.  Both switches were MEASURED and are off (profiles/r02_siblings.txt):
+// the range guards the reference's degenerate-geometry behaviour needs around fm::root /
+// fm::div_fast cost more issue slots than the shorter sequences save -- with both on, gz ran
+// 2 % and the tensor / magnetic sets 6 % SLOWER than with the library's sqrt() and IEEE
+// divisions (whose own slow paths sit behind one predicated call each).
+#ifndef FB200_PP_SQRT
+#define FB200_PP_SQRT 0        // 1: fm::root on its range (same bits as sqrt()), sqrt() outside
+#endif
+#ifndef FB200_PP_DIV
+#define FB200_PP_DIV 0         // 1: fm::div_fast for mid-range operands, IEEE division outside
+#endif
+FB_HD double pp_sqrt(double a)
+{
+#if FB200_PP_SQRT
+    if ((unsigned)fm::hi32(a) - 0x03500000u < 0x7ca00000u) return fm::root(a);
+#endif
+    return sqrt(a);
+}
+
+// a / b: reciprocal seed + Newton step + residual correction (fm::div_fast, within an ulp of
+// the IEEE quotient) when both exponents lie in [2^-511, 2^512) -- no overflow, underflow or
+// special value can occur on that path; the IEEE division for everything else (zero
+// numerators, infinities, NaN, the extremes)
+FB_HD bool pp_midrange(double v)
+{
+    return ((unsigned)fm::hi32(v) & 0x7ff00000u) - 0x20000000u < 0x40000000u;
+}
+FB_HD double pp_div(double a, double b)
+{
+#if FB200_PP_DIV
+    if (pp_midrange(a) && pp_midrange(b)) return fm::div_fast(a, b);
+#endif
+    return a / b;
+}
+
 FB_HD double pp_log(double x)
 {
     if (x > 0.0 && pp_ordinary(x)) return fm::log_tab(x);        // division-free, 10 FP64 instructions
@@ -85,86 +120,86 @@ struct EvalPolyEdge {
             const double Q1 = (Y2 - Y1) * Y1 + (X2 - X1) * X1;
             const double Q2 = (Y2 - Y1) * Y2 + (X2 - X1) * X2;
             const double A1s = X1 * X1 + Y1 * Y1, A2s = X2 * X2 + Y2 * Y2;
-            const double R11 = sqrt(A1s + Z1_sqr), R12 = sqrt(A2s + Z1_sqr);
-            const double R21 = sqrt(A1s + Z2_sqr), R22 = sqrt(A2s + Z2_sqr);
-            const double A1 = sqrt(A1s), A2 = sqrt(A2s);
-            const double B1 = sqrt(Q1 * Q1 + p_sqr), B2 = sqrt(Q2 * Q2 + p_sqr);
+            const double R11 = pp_sqrt(A1s + Z1_sqr), R12 = pp_sqrt(A2s + Z1_sqr);
+            const double R21 = pp_sqrt(A1s + Z2_sqr), R22 = pp_sqrt(A2s + Z2_sqr);
+            const double A1 = pp_sqrt(A1s), A2 = pp_sqrt(A2s);
+            const double B1 = pp_sqrt(Q1 * Q1 + p_sqr), B2 = pp_sqrt(Q2 * Q2 + p_sqr);
             const double E11 = R11 * B1, E12 = R12 * B2, E21 = R21 * B1, E22 = R22 * B2;
             double k = (Z2 - Z1) * (pp_atan2(Q2, p) - pp_atan2(Q1, p));
             k = k + Z2 * (pp_atan2(Z2 * Q1, R21 * p) - pp_atan2(Z2 * Q2, R22 * p));
             k = k + Z1 * (pp_atan2(Z1 * Q2, R12 * p) - pp_atan2(Z1 * Q1, R11 * p));
             const double C1 = Q1 * A1, C2 = Q2 * A2;
-            k = k + 0.5 * p * A1 / (B1 + d) *
-                        pp_log((E11 - C1) * (E21 + C1) / ((E11 + C1) * (E21 - C1) + d) + d);
-            k = k + 0.5 * p * (A2 / (B2 + d)) *
-                        pp_log((E22 - C2) * (E12 + C2) / ((E22 + C2) * (E12 - C2) + d) + d);
+            k = k + pp_div(0.5 * p * A1, B1 + d) *
+                        pp_log(pp_div((E11 - C1) * (E21 + C1), (E11 + C1) * (E21 - C1) + d) + d);
+            k = k + 0.5 * p * pp_div(A2, B2 + d) *
+                        pp_log(pp_div((E22 - C2) * (E12 + C2), (E22 + C2) * (E12 - C2) + d) + d);
             acc[c] = acc[c] + k * p0;
             ++c;
         }
         if constexpr (need_a || need_l || need_zz) {
             const double v1 = X1 * X1 + Y1 * Y1, v2 = X2 * X2 + Y2 * Y2;
-            const double R11 = sqrt(v1 + Z1_sqr), R12 = sqrt(v1 + Z2_sqr);
-            const double R21 = sqrt(v2 + Z1_sqr), R22 = sqrt(v2 + Z2_sqr);
+            const double R11 = pp_sqrt(v1 + Z1_sqr), R12 = pp_sqrt(v1 + Z2_sqr);
+            const double R21 = pp_sqrt(v2 + Z1_sqr), R22 = pp_sqrt(v2 + Z2_sqr);
             double exx = 0, exy = 0, exz = 0, eyy = 0, eyz = 0, ezz = 0;
             if constexpr (need_zz) {                                // polyprism.py:1054-1075
                 const double dx = X2 - X1, dy = Y2 - Y1;
-                const double dist = sqrt(dx * dx + dy * dy) + d;
-                const double p = (X1 * Y2 - X2 * Y1) / dist;
-                const double d1 = (dx * X1 + dy * Y1) / dist, d2 = (dx * X2 + dy * Y2) / dist;
+                const double dist = pp_sqrt(dx * dx + dy * dy) + d;
+                const double p = pp_div(X1 * Y2 - X2 * Y1, dist);
+                const double d1 = pp_div(dx * X1 + dy * Y1, dist), d2 = pp_div(dx * X2 + dy * Y2, dist);
                 ezz = pp_atan2(Z2 * d2, p * R22) - pp_atan2(Z1 * d2, p * R21) - pp_atan2(Z2 * d1, p * R12) +
                       pp_atan2(Z1 * d1, p * R11);
             }
             if constexpr (need_a || need_l) {
                 const double dx = X2 - X1 + d, dy = Y2 - Y1 + d;
-                const double dist = sqrt(dx * dx + dy * dy);
-                const double d1 = (dx * X1 + dy * Y1) / dist + d, d2 = (dx * X2 + dy * Y2) / dist + d;
-                const double n = dx / dy, m = dy / dx;
+                const double dist = pp_sqrt(dx * dx + dy * dy);
+                const double d1 = pp_div(dx * X1 + dy * Y1, dist) + d, d2 = pp_div(dx * X2 + dy * Y2, dist) + d;
+                const double n = pp_div(dx, dy), m = pp_div(dy, dx);
                 if constexpr (need_l) {
-                    const double log_r22 = pp_log((R22 - d2) / (R22 + d2) + d);
-                    const double log_r21 = pp_log((R21 - d2) / (R21 + d2) + d);
-                    const double log_r12 = pp_log((R12 - d1) / (R12 + d1) + d);
-                    const double log_r11 = pp_log((R11 - d1) / (R11 + d1) + d);
+                    const double log_r22 = pp_log(pp_div(R22 - d2, R22 + d2) + d);
+                    const double log_r21 = pp_log(pp_div(R21 - d2, R21 + d2) + d);
+                    const double log_r12 = pp_log(pp_div(R12 - d1, R12 + d1) + d);
+                    const double log_r11 = pp_log(pp_div(R11 - d1, R11 + d1) + d);
                     if constexpr (need_xz) {                        // polyprism.py:791-824
                         const double n_sqr_p1 = n * n + 1;
                         const double g = X1 - Y1 * n, ng = n * g;
-                        const double ld1 = (0.5 / d1) * (log_r12 - log_r11);
-                        const double ld2 = (0.5 / d2) * (log_r22 - log_r21);
+                        const double ld1 = pp_div(0.5, d1) * (log_r12 - log_r11);
+                        const double ld2 = pp_div(0.5, d2) * (log_r22 - log_r21);
                         double t = (Y2 * n_sqr_p1 + ng) * ld2;
                         t = t - (Y1 * n_sqr_p1 + ng) * ld1;
-                        exz = t * (-1 / n_sqr_p1);
+                        exz = t * pp_div(-1.0, n_sqr_p1);
                     }
                     if constexpr (need_yz) {                        // polyprism.py:967-997
                         const double m_sqr_p1 = m * m + 1;
                         const double cc = Y1 - X1 * m, cm = cc * m;
-                        double t = (X2 * m_sqr_p1 + cm) * (0.5 / d2) * (log_r22 - log_r21);
-                        t = t - (X1 * m_sqr_p1 + cm) * (0.5 / d1) * (log_r12 - log_r11);
-                        eyz = t * (1 / m_sqr_p1);
+                        double t = (X2 * m_sqr_p1 + cm) * pp_div(0.5, d2) * (log_r22 - log_r21);
+                        t = t - (X1 * m_sqr_p1 + cm) * pp_div(0.5, d1) * (log_r12 - log_r11);
+                        eyz = t * pp_div(1.0, m_sqr_p1);
                     }
                 }
                 if constexpr (need_a) {
-                    const double p = (X1 * Y2 - X2 * Y1) / dist + d;
+                    const double p = pp_div(X1 * Y2 - X2 * Y1, dist) + d;
                     const double ad2 = pp_atan2(Z2 * d2, p * R22) - pp_atan2(Z1 * d2, p * R21);
                     const double ad1 = pp_atan2(Z2 * d1, p * R12) - pp_atan2(Z1 * d1, p * R11);
                     if constexpr (need_xx) {                        // polyprism.py:617-647
                         const double g = X1 - Y1 * n;
-                        double t = g * Y2 * ad2 / (p * d2) + n * p * ad2 / (d2);
-                        t = t - (g * Y1 * ad1 / (p * d1) + n * p * ad1 / (d1));
-                        t = t + n * pp_log((Z2 + R12) * (Z1 + R21) / ((Z1 + R11) * (Z2 + R22) + d) + d);
-                        exx = t * (-1 / (1 + n * n));
+                        double t = pp_div(g * Y2 * ad2, p * d2) + pp_div(n * p * ad2, d2);
+                        t = t - (pp_div(g * Y1 * ad1, p * d1) + pp_div(n * p * ad1, d1));
+                        t = t + n * pp_log(pp_div((Z2 + R12) * (Z1 + R21), (Z1 + R11) * (Z2 + R22) + d) + d);
+                        exx = t * pp_div(-1.0, 1 + n * n);
                     }
                     if constexpr (need_xy) {                        // polyprism.py:703-734
                         const double g = X1 - Y1 * n, g_sqr = g * g;
-                        double t = (g_sqr + g * n * Y2) * ad2 / (p * d2) - p * ad2 / d2;
-                        t = t - ((g_sqr + g * n * Y1) * ad1 / (p * d1) - p * ad1 / d1);
-                        t = t + pp_log((Z2 + R22) * (Z1 + R11) / ((Z1 + R21) * (Z2 + R12) + d) + d);
-                        exy = t * (1 / (1 + n * n));
+                        double t = pp_div((g_sqr + g * n * Y2) * ad2, p * d2) - pp_div(p * ad2, d2);
+                        t = t - (pp_div((g_sqr + g * n * Y1) * ad1, p * d1) - pp_div(p * ad1, d1));
+                        t = t + pp_log(pp_div((Z2 + R22) * (Z1 + R11), (Z1 + R21) * (Z2 + R12) + d) + d);
+                        exy = t * pp_div(1.0, 1 + n * n);
                     }
                     if constexpr (need_yy) {                        // polyprism.py:880-910
                         const double cc = Y1 - X1 * m;
-                        double t = cc * X2 * ad2 / (p * d2) + m * p * ad2 / d2;
-                        t = t - (cc * X1 * ad1 / (p * d1) + m * p * ad1 / d1);
-                        t = t + m * pp_log((Z2 + R12) * (Z1 + R21) / ((Z2 + R22) * (Z1 + R11)) + d);
-                        eyy = t * (1 / (1 + m * m));
+                        double t = pp_div(cc * X2 * ad2, p * d2) + pp_div(m * p * ad2, d2);
+                        t = t - (pp_div(cc * X1 * ad1, p * d1) + pp_div(m * p * ad1, d1));
+                        t = t + m * pp_log(pp_div((Z2 + R12) * (Z1 + R21), (Z2 + R22) * (Z1 + R11)) + d);
+                        eyy = t * pp_div(1.0, 1 + m * m);
                     }
                 }
             }

@@ -1,6 +1,7 @@
 """
-Prism containers of the forward-model path: ``Prism``, ``PrismMesh`` and
-``PrismRelief``.
+Containers of the forward-model path: ``Prism``, ``PrismMesh``, ``PrismRelief`` and, for the
+sibling kernels, ``Sphere``, ``PolygonalPrism`` and ``PointGrid`` (the equivalent layer's
+grid of point sources, mesh.py:186-388).
 
 They behave like the reference's classes (fatiando/mesher/geometry.py:170-260,
 fatiando/mesher/mesh.py:391-492 and :495-665): iterables / sequences of
@@ -118,6 +119,96 @@ class PolygonalPrism(object):
 
     def copy(self):
         return PolygonalPrism(np.transpose([self.x, self.y]), self.z1, self.z2, props=dict(self.props))
+
+
+class PointGrid(object):
+    """
+    A regular grid of point sources: spheres of unit volume (mesh.py:186-388), what the
+    equivalent layer is made of (eqlayer.py:100-111).  A sequence of :class:`Sphere`, rows
+    along x (north), columns along y; ``z`` a number or one value per point.
+
+    >>> g = PointGrid([0, 10, 2, 6], 200, (2, 3))
+    >>> g.shape, g.size, (g.dx, g.dy)
+    ((2, 3), 6, (10.0, 2.0))
+    >>> [list(map(float, p.center)) for p in g][1::4]
+    [[0.0, 4.0, 200.0], [10.0, 6.0, 200.0]]
+    >>> z = np.linspace(0, 1100, 12)
+    >>> g = PointGrid((0, 3, 0, 2), z, (4, 3))
+    >>> g.addprop('bla', np.arange(1, 13))
+    >>> [(s.props['bla'].tolist(), s.x.tolist(), s.y.tolist(), s.z.tolist()) for s in g.split((2, 3))][4]
+    ([8, 11], [2.0, 3.0], [1.0, 1.0], [700.0, 1000.0])
+    """
+
+    def __init__(self, area, z, shape, props=None):
+        from . import gridder
+        self.area = area
+        self.shape = shape
+        self.props = props if props is not None else {}
+        nx, ny = shape
+        self.size = nx * ny
+        self.z = np.zeros(self.size) + z
+        self.radius = float(np.cbrt(3. / (4. * np.pi)))          # unit volume
+        self.x, self.y = gridder.regular(area, shape)
+        with np.errstate(all='ignore'):        # a one-point row or column has no spacing (nan), like the reference
+            self.dx, self.dy = gridder.spacing(area, shape)
+        self.i = 0
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, index):
+        if not isinstance(index, (int, np.integer)):
+            raise IndexError('Invalid index type. Should be int.')
+        if index >= self.size or index < -self.size:
+            raise IndexError('Grid index out of range.')
+        if index < 0:
+            index += self.size
+        return Sphere(self.x[index], self.y[index], self.z[index], self.radius,
+                      props={p: self.props[p][index] for p in self.props})
+
+    def __iter__(self):
+        self.i = 0
+        return self
+
+    def __next__(self):
+        if self.i >= self.size:
+            raise StopIteration
+        point = self[self.i]
+        self.i += 1
+        return point
+
+    next = __next__
+
+    def addprop(self, prop, values):
+        """One value of ``prop`` per point of the grid."""
+        self.props[prop] = values
+
+    def split(self, shape):
+        """
+        The grid cut into ``shape = (nx, ny)`` subgrids (a list of :class:`PointGrid`, x blocks
+        outermost); both counts must divide the grid's.
+        """
+        nx, ny = shape
+        totalx, totaly = self.shape
+        if totalx % nx != 0 or totaly % ny != 0:
+            raise ValueError('Cannot split! nx and ny must be divisible by grid shape')
+        x1, x2, y1, y2 = self.area
+        mx, my = totalx // nx, totaly // ny
+        xstarts = np.linspace(x1, x2, totalx)[::mx]
+        ystarts = np.linspace(y1, y2, totaly)[::my]
+        lx, ly = self.dx * (mx - 1), self.dy * (my - 1)
+        zgrid = np.reshape(self.z, self.shape)
+        pgrids = {p: np.reshape(self.props[p], self.shape) for p in self.props}
+        parts = []
+        for i, xs in enumerate(xstarts):
+            for j, ys in enumerate(ystarts):
+                block = (slice(i * mx, (i + 1) * mx), slice(j * my, (j + 1) * my))
+                parts.append(PointGrid([xs, xs + lx, ys, ys + ly], zgrid[block].ravel(), (mx, my),
+                                       {p: pgrids[p][block].ravel() for p in pgrids}))
+        return parts
+
+    def copy(self):
+        return _copy.deepcopy(self)
 
 
 class _PrismSequence(object):
@@ -266,6 +357,49 @@ class PrismMesh(_PrismSequence):
         """Iterate over the layers."""
         for i in range(self.shape[0]):
             yield self.get_layer(i)
+
+    def dump(self, meshfile, propfile, prop):
+        """
+        Write the mesh and one property in the text format of UBC-GIF's MeshTools3D
+        (mesh.py:831-891): the mesh file holds ``ny nx nz``, the origin ``y1 x1 -z1`` and the
+        cell sizes as ``count*size`` per axis; the property file one value per line with z
+        fastest, then x, then y (Fortran order of the ``(nz, ny, nx)`` array), ``%.4f``,
+        masked cells as -10000000.  ``meshfile`` / ``propfile``: file names or open files.
+
+        >>> from io import StringIO
+        >>> meshfile, densfile = StringIO(), StringIO()
+        >>> mesh = PrismMesh((0, 10, 0, 20, 0, 5), (1, 2, 2))
+        >>> mesh.addprop('density', [1, 2, 3, 4])
+        >>> mesh.dump(meshfile, densfile, 'density')
+        >>> print(meshfile.getvalue().strip())
+        2 2 1
+        0 0 0
+        2*10
+        2*5
+        1*5
+        >>> print(densfile.getvalue().strip())
+        1.0000
+        3.0000
+        2.0000
+        4.0000
+        """
+        if prop not in self.props:
+            raise ValueError("mesh doesn't have a '%s' property." % (prop))
+        nz, ny, nx = self.shape
+        dx, dy, dz = self.dims
+        header = ["%d %d %d" % (ny, nx, nz),
+                  "%g %g %g" % (self.bounds[2], self.bounds[0], -self.bounds[4]),
+                  "%d*%g" % (ny, dy), "%d*%g" % (nx, dx), "%d*%g" % (nz, dz)]
+        text = "\n".join(header)              # no newline after the last line, like the reference
+        if isinstance(meshfile, str):
+            with open(meshfile, 'w') as f:
+                f.write(text)
+        else:
+            meshfile.write(text)
+        values = np.array([float(v) for v in self.props[prop]], dtype=np.float64)
+        if len(self.mask):
+            values[np.asarray(self.mask, dtype=np.int64)] = -10000000
+        np.savetxt(propfile, values.reshape(self.shape).ravel(order='F'), fmt='%.4f')
 
 
 class PrismRelief(_PrismSequence):

@@ -23,8 +23,24 @@ GRAVITY_FIELDS = ('gz', 'gxx', 'gxy', 'gxz', 'gyy', 'gyz', 'gzz')
 MAGNETIC_FIELDS = ('tf', 'bx', 'by', 'bz')
 
 
+def _is_point_grid(model):
+    """The reference's PointGrid or ours: x, y, z arrays, one radius, per-point property lists."""
+    return all(hasattr(model, a) for a in ('area', 'shape', 'radius', 'x', 'y', 'z', 'props', 'dx', 'dy'))
+
+
 def _flatten(spheres, prop, override):
     """SoA arrays of the spheres a field with property ``prop`` sums (sphere.py:351-357)."""
+    if _is_point_grid(spheres) and (override or prop is None or prop in spheres.props):
+        # a PointGrid (the equivalent layer, mesh.py:186-388): its arrays ARE the SoA form
+        n = spheres.size
+        geo = [numpy.ascontiguousarray(a, dtype=numpy.float64) for a in
+               (spheres.x, spheres.y, spheres.z, numpy.zeros(n) + spheres.radius)]
+        dens = mag = None
+        if not override and prop == 'density':
+            dens = numpy.ascontiguousarray(spheres.props['density'], dtype=numpy.float64)
+        if not override and prop == 'magnetization':
+            mag = numpy.ascontiguousarray(spheres.props['magnetization'], dtype=numpy.float64).reshape(-1, 3)
+        return geo, dens, mag
     keep = [s for s in spheres
             if s is not None and (override or prop is None or prop in s.props)]
     geo = numpy.array([[s.x, s.y, s.z, s.radius] for s in keep], dtype=numpy.float64).reshape(-1, 4)
@@ -143,6 +159,10 @@ def jacobian(xp, yp, zp, spheres, field='gz', inc=None, dec=None, pmag=None, tra
             if fvec is None:
                 raise ValueError("magnetic Jacobians need pmag or inc, dec")
             pmag = fvec
+    if _is_point_grid(spheres):
+        # the equivalent layer itself (eqlayer.py:108-110 walks it point by point)
+        with Model(spheres, None, keep_all=True, device=device) as model:
+            return model.jacobian(xp, yp, zp, field, pmag=pmag, fvec=fvec, transposed=transposed)
     spheres = list(spheres)
     kept = [i for i, s in enumerate(spheres) if s is not None]
     with Model(spheres, None, keep_all=True, device=device) as model:

@@ -184,3 +184,72 @@ def test_doctests_of_the_host_modules():
     for mod in (utils, mesher):
         res = doctest.testmod(mod)
         assert res.failed == 0 and res.attempted > 0, mod.__name__
+
+
+def test_kernel_profiles_are_valid_for_this_tree():
+    """
+    bench.py's roofline reads executed-instruction counts from profiles/r02_kernel_<key>.json and
+    refuses a file measured on other sources of that kernel (bench.load_profile).  Every committed
+    profile must be valid for the committed sources: a kernel change without a re-capture
+    (tools/profile_all.py) fails here, on the CPU, before a bench line carries `frac: null`.
+    """
+    import glob
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_kernel_*.json")))
+    assert len(files) >= 14
+    for path in files:
+        d = json.load(open(path))
+        key = d["key"]
+        assert key in bench.KERNEL_TU, key
+        # the hashed set really is the kernel's: its translation unit and the launch code
+        names = [os.path.basename(f) for f in bench.kernel_sources(key)]
+        assert bench.KERNEL_TU[key] in names and "prism_abi.cu" in names and "fatiando_b200.h" in names
+        prof, src = bench.load_profile(key)
+        assert prof is not None, src
+    # a header of another kernel family is not part of a prism kernel's hash
+    assert "polyprism.cuh" not in [os.path.basename(f) for f in bench.kernel_sources("c2_nodes")]
+    assert "polyprism.cuh" in [os.path.basename(f) for f in bench.kernel_sources("polyprism_gz")]
+
+
+def test_point_grid_and_mesh_dump_match_the_reference():
+    """PointGrid (mesh.py:186-388) and PrismMesh.dump (mesh.py:831-891) against the real reference's outputs."""
+    import io
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "containers.npz")))
+    grid = mesher.PointGrid(tuple(g['pg_area']), g['pg_zin'], tuple(int(v) for v in g['pg_shape']))
+    grid.addprop('density', g['pg_density'])
+    for name, ours in (('pg_x', grid.x), ('pg_y', grid.y), ('pg_z', grid.z)):
+        assert np.array_equal(g[name], ours), name
+    assert grid.radius == float(g['pg_radius']) and [grid.dx, grid.dy] == list(g['pg_spacing'])
+    assert len(grid) == 24 and len(list(grid)) == 24
+    items = [grid[i] for i in (0, 5, -1)]
+    assert np.array_equal(g['pg_items'], [[s.x, s.y, s.z, s.radius, s.props['density']] for s in items])
+    parts = grid.split((3, 2))
+    assert len(parts) == int(g['pg_split_n'])
+    for k, s in enumerate(parts):
+        assert np.array_equal(g['pg_split_%d' % k], [s.x, s.y, s.z, s.props['density']]), k
+        assert np.array_equal(g['pg_split_area_%d' % k], s.area), k
+    with pytest.raises(ValueError):
+        grid.split((4, 2))
+    with pytest.raises(IndexError):
+        grid[24]
+    flat = mesher.PointGrid((0, 10, 2, 6), 200, (2, 3))
+    assert np.array_equal(g['pg_flat'], [flat.x, flat.y, flat.z])
+    # the sphere flattener takes the grid's arrays as they are
+    from fatiando_b200 import sphere
+    geo, dens, mag = sphere._flatten(grid, 'density', False)
+    listed = sphere._flatten(list(grid), 'density', False)
+    assert all(np.array_equal(a, b) for a, b in zip(geo, listed[0])) and np.array_equal(dens, listed[1])
+
+    mesh = mesher.PrismMesh(tuple(g['dump_bounds']), tuple(int(v) for v in g['dump_shape']))
+    mesh.addprop('density', g['dump_density'])
+    for tag, mask in (('plain', []), ('masked', g['dump_mask'].tolist())):
+        mesh.mask = list(mask)
+        mf, pf = io.StringIO(), io.StringIO()
+        mesh.dump(mf, pf, 'density')
+        assert mf.getvalue() == g['dump_%s_mesh' % tag].tobytes().decode(), tag
+        assert pf.getvalue() == g['dump_%s_prop' % tag].tobytes().decode(), tag
+    with pytest.raises(ValueError):
+        mesh.dump(io.StringIO(), io.StringIO(), 'magnetization')

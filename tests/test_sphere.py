@@ -143,3 +143,30 @@ def test_sphere_cloud_fused_overrides_and_jacobian(gpu_lib):
     q = int(np.nonzero(g['many_kind'] != 0)[0][3])
     want = so.model('tf', x, y, z, g['many_geo'][q:q + 1], np.array([fv]), fvec=fv)
     np.testing.assert_allclose(jt[q], want, rtol=1e-11, atol=1e-14 * np.abs(want).max())
+
+
+@pytest.mark.gpu
+def test_equivalent_layer_of_a_point_grid(gpu_lib):
+    """
+    eqlayer.py:100-111: the Jacobian of a PointGrid layer, column i = gz of point source i with
+    unit density -- and the layer's field with its own densities -- from the grid's arrays
+    (no per-point Sphere objects), against the numpy oracle.
+    """
+    from fatiando_b200 import sphere, gridder
+    from fatiando_b200.mesher import PointGrid
+    from oracle import sphere_oracle as so
+    layer = PointGrid((-500., 500., -400., 600.), np.linspace(150., 210., 63), (9, 7))
+    rs = np.random.RandomState(11)
+    layer.addprop('density', rs.uniform(-300, 300, layer.size))
+    x, y, z = gridder.scatter((-600, 600, -600, 600), 300, z=-20., seed=5)
+    geo = np.transpose([layer.x, layer.y, layer.z, np.zeros(layer.size) + layer.radius])
+    jac = sphere.jacobian(x, y, z, layer, 'gz')
+    assert jac.shape == (300, 63)
+    for q in (0, 17, 62):
+        want = so.model('gz', x, y, z, geo[q:q + 1], np.array([1.0]))
+        np.testing.assert_allclose(jac[:, q], want, rtol=1e-12, atol=1e-15 * np.abs(want).max())
+    assert np.array_equal(jac, sphere.jacobian(x, y, z, list(layer), 'gz'))
+    dens = np.asarray(layer.props['density'])
+    got = sphere.gz(x, y, z, layer)
+    _close(got, so.model('gz', x, y, z, geo, dens), so.model('gz', x, y, z, geo, dens, terms=True), 'layer gz')
+    _close(jac @ dens, got, np.abs(jac) @ np.abs(dens), 'J rho')

@@ -1,6 +1,7 @@
 """
 Throughput of the sibling families (spheres, polygonal prisms) through the Python API with
-host buffers.  python tools/bench_siblings.py
+host buffers.  python tools/bench_siblings.py [sphere|polyprism [NBODIES]]
+(NBODIES: a smaller model for an ncu capture -- the per-pair counts do not depend on it)
 """
 import os
 import sys
@@ -15,12 +16,13 @@ from fatiando_b200.mesher import PolygonalPrism, Sphere   # noqa: E402
 
 def main():
     rs = np.random.RandomState(0)
+    nbodies = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     t = np.linspace(0, 2 * np.pi, 20, endpoint=False)[::-1]
     polys = [PolygonalPrism(np.transpose([cx + 80 * np.cos(t), cy + 60 * np.sin(t)]), 50, 400,
                             {"density": 500., "magnetization": [1., 2., 3.]})
-             for cx, cy in rs.uniform(0, 1e4, (5000, 2))]
+             for cx, cy in rs.uniform(0, 1e4, (nbodies or 5000, 2))]
     spheres = [Sphere(rs.uniform(0, 1e4), rs.uniform(0, 1e4), rs.uniform(100, 2000), 20.,
-                      {"density": 500., "magnetization": [1., 2., 3.]}) for _ in range(100000)]
+                      {"density": 500., "magnetization": [1., 2., 3.]}) for _ in range(nbodies or 100000)]
     x, y, z = gridder.regular((0, 1e4, 0, 1e4), (400, 400), z=-50)
     sets = ((["gz"], "density"), (["gxx", "gxy", "gxz", "gyy", "gyz", "gzz"], "density"),
             (["tf", "bx", "by", "bz"], "magnetization"))

@@ -48,8 +48,8 @@ CASES = {
 
 
 SIBLINGS = {"sphere_gz": ("sphere", 1e5 * 1.6e5, "spheres: forward_kernel<0x008,EvalSphere>, 1e5 spheres x 400x400 points"),
-            "polyprism_gz": ("polyprism", 1e5 * 1.6e5, "polygonal prisms: forward_kernel<0x008,EvalPolyEdge>, 5000 prisms x 20 "
-                                                     "edges x 400x400 points (rows = edges)")}
+            "polyprism_gz": ("polyprism 500", 1e4 * 1.6e5, "polygonal prisms: forward_kernel<0x008,EvalPolyEdge>, 500 prisms x 20 "
+                                                         "edges x 400x400 points (rows = edges)")}
 
 
 def _title_pairs(key):
@@ -72,7 +72,7 @@ def gpu(keys):
     for key in keys:
         rep = os.path.join(out, "r02_" + key)
         if key in SIBLINGS:
-            target = [os.path.join(ROOT, "tools", "bench_siblings.py"), SIBLINGS[key][0]]
+            target = [os.path.join(ROOT, "tools", "bench_siblings.py")] + SIBLINGS[key][0].split()
             regex = "forward_kernel"
         else:
             wl, extra, regex, _, _ = CASES[key]
