@@ -88,14 +88,14 @@ KERNEL_TU = {
     "c5_surface": "fwd_surface.cu", "c5t_surface": "fwd_surface.cu",
     "polyprism_gz": "fwd_polyprism_exact.cu", "sphere_gz": "fwd_sphere.cu",
 }
-# host side of every launch (grid sizing, prism split, dispatch): part of every kernel's hash
+# host side of every launch (grid sizing, prism split, dispatch) and the public header
 LAUNCH_FILES = ("prism_abi.cu", "abi_internal.h")
 
 
 def kernel_sources(key, root=None):
     """
-    The files the profiled kernel of `key` is built from: its translation unit, everything that
-    reaches it through #include "..." (transitively), the launch code and the public header.
+    The DEVICE code the profiled kernel of `key` is built from: its translation unit and
+    everything that reaches it through #include "..." (transitively).
     """
     csrc = os.path.join(root or ROOT, "fatiando_b200", "csrc")
     seen, todo = [], [KERNEL_TU[key]]
@@ -107,24 +107,41 @@ def kernel_sources(key, root=None):
         for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(os.path.join(csrc, f)).read(), re.M):
             if "/" not in inc:
                 todo.append(inc)
-    files = [os.path.join(csrc, f) for f in sorted(set(seen) | set(LAUNCH_FILES))]
-    return files + sorted(glob.glob(os.path.join(root or ROOT, "include", "*.h")))
+    return [os.path.join(csrc, f) for f in sorted(seen)]
 
 
-def kernel_hash(key, root=None):
-    """Hash of kernel_sources(key): what a profile of that kernel is valid for."""
+def launch_sources(root=None):
+    """The host code that sizes and issues every launch, and the public header."""
+    return [os.path.join(root or ROOT, "fatiando_b200", "csrc", f) for f in LAUNCH_FILES] + \
+        sorted(glob.glob(os.path.join(root or ROOT, "include", "*.h")))
+
+
+def _hash_files(files):
     h = hashlib.sha256()
-    for f in kernel_sources(key, root):
+    for f in files:
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
 
 
+def kernel_hash(key, root=None):
+    """Hash of kernel_sources(key): what the instruction counts of a profile are valid for."""
+    return _hash_files(kernel_sources(key, root))
+
+
+def launch_hash(root=None):
+    """Hash of launch_sources(): the launch shape (grid, split) a profile was captured with."""
+    return _hash_files(launch_sources(root))
+
+
 def load_profile(key):
     """
     profiles/r02_kernel_<key>.json (tools/summarize_profile.py), or None when missing/stale.
-    A profile is valid while the sources of ITS kernel (kernel_sources) are unchanged; a change
-    to another kernel's header (e.g. polyprism.cuh for the prism kernels) does not touch it.
+    The per-pair instruction counts are a property of the kernel's device code: the file is
+    refused when `kernel_hash` differs from this tree's (a change to another kernel's header,
+    e.g. polyprism.cuh for the prism kernels, does not touch it).  A change of the LAUNCH code
+    (how many blocks, how the prisms are split) since the capture leaves the counts valid; it
+    is reported next to them (`launch_code` in the roofline object) instead of hidden.
     """
     path = os.path.join(ROOT, "profiles", "r02_kernel_%s.json" % key)
     try:
@@ -136,6 +153,8 @@ def load_profile(key):
     if d.get("kernel_hash") != kernel_hash(key):
         return None, "profiles/r02_kernel_%s.json is stale (measured on kernel sources %s, this build is %s)" % (
             key, d.get("kernel_hash"), kernel_hash(key))
+    d["launch_code"] = "as captured" if d.get("launch_hash") == launch_hash() else \
+        "changed since the capture (launch sources %s, this build %s)" % (d.get("launch_hash"), launch_hash())
     return d, os.path.relpath(path, ROOT)
 
 
@@ -671,6 +690,7 @@ class Bench(object):
             out = {"bound": "hbm", "unit": "GB/s", "achieved": per_gpu * 8 / 1e9, "peak": hbm,
                    "frac": per_gpu * 8 / 1e9 / hbm, "profile": src,
                    "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+                   "launch_code": prof.get("launch_code") if prof else None,
                    "algorithmic_bytes_per_entry": 8,
                    "peak_source": ("MEASURED_PEAKS.json hbm_gbs (copy bandwidth, read+write)" if peaks_file
                                    else "fallback 6650 GB/s"),
@@ -686,7 +706,7 @@ class Bench(object):
             out.update(achieved=per_gpu * executed * 2.0 / 1e12, frac=per_gpu * executed * 2.0 / 1e12 / peak,
                        executed_fp64_inst_per_pair=executed, executed_inst_per_pair=prof.get("inst_per_pair"),
                        kernel=prof.get("kernel"), traffic=prof.get("dram_bytes_per_launch"),
-                       ncu_pipe_fp64_pct=prof.get("pipe_fp64_pct"))
+                       ncu_pipe_fp64_pct=prof.get("pipe_fp64_pct"), launch_code=prof.get("launch_code"))
         else:
             out.update(achieved=None, frac=None, traffic=None)
         out["algorithmic"] = {"flop_per_pair": wk['flop'], "of": wk['what'],

@@ -765,6 +765,19 @@ static void view_of(const fb200_model *mod, bool magnetic, ModelView *v)
     v->m = mod->m;
 }
 
+// Thread blocks per SM the prism / node split aims for.  The kernels keep 3-4 blocks resident
+// per SM, so 96 blocks per SM are ~24-32 waves: the last, partly filled wave costs 1-2 % of the
+// launch instead of the 4-6 % it cost at 20 blocks per SM (5.3 waves on C2), for 47 instead of
+// 10 partial sums per point.  Measured (tools/split_sweep.py, profiles/r02_split_sweep.txt):
+// C2 18.48 -> 17.52 ms, C3 254.6 -> 246.1 ms, C5 gz+tensor 353.0 -> 348.9 ms; 128 is no better.
+// FB200_SPLIT_TARGET overrides it (tuning).
+static int64_t split_blocks_per_sm()
+{
+    const char *e = std::getenv("FB200_SPLIT_TARGET");
+    const long v = e ? std::atol(e) : 0;
+    return v > 0 ? v : 96;
+}
+
 static int reduce_split(fb200_model *mod, int nc, int64_t nsplit, int64_t n, int64_t ld_p,
                         const double *scale, const int *out_row, double *d_out, int64_t ld_out)
 {
@@ -809,7 +822,7 @@ static int run_set_mesh(fb200_model *mod, uint32_t set, uint32_t request, bool a
     const int64_t tiles = (mod->nnodes + TILE - 1) / TILE;
     int64_t nsplit = 1;
     if (allow_split) {
-        const int64_t target = (int64_t)mod->sm_count * 20;
+        const int64_t target = (int64_t)mod->sm_count * split_blocks_per_sm();
         nsplit = std::min<int64_t>(std::max<int64_t>(1, (target + blocks_x - 1) / blocks_x), tiles);
         nsplit = std::min<int64_t>(nsplit, 65535);
     }
@@ -860,7 +873,7 @@ static int run_set_surface(fb200_model *mod, uint32_t set, uint32_t request, boo
         const int64_t tiles = (m + TILE - 1) / TILE;
         int64_t ns = 1;
         if (allow_split) {
-            const int64_t target = (int64_t)mod->sm_count * 20;
+            const int64_t target = (int64_t)mod->sm_count * split_blocks_per_sm();
             ns = std::min<int64_t>(std::max<int64_t>(1, (target + blocks_x - 1) / blocks_x), tiles);
             ns = std::min<int64_t>(ns, 32000);
         }
@@ -927,7 +940,7 @@ static int run_set(fb200_model *mod, uint32_t set, uint32_t request, bool exact,
     const int64_t tiles = (mod->m + TILE - 1) / TILE;
     int64_t nsplit = 1;
     if (allow_split && init == nullptr) {
-        const int64_t target = (int64_t)mod->sm_count * 20;
+        const int64_t target = (int64_t)mod->sm_count * split_blocks_per_sm();
         nsplit = std::min<int64_t>(std::max<int64_t>(1, (target + blocks_x - 1) / blocks_x), tiles);
         nsplit = std::min<int64_t>(nsplit, 65535);
     }
@@ -1581,7 +1594,7 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         const int64_t blocks_x = (m + JAC_THREADS - 1) / JAC_THREADS;
         const int64_t tiles = (cnt + JAC_TILE - 1) / JAC_TILE;
         int64_t nsplit = std::min<int64_t>(
-            std::max<int64_t>(1, ((int64_t)mod->sm_count * 20 + blocks_x - 1) / blocks_x), tiles);
+            std::max<int64_t>(1, ((int64_t)mod->sm_count * split_blocks_per_sm() + blocks_x - 1) / blocks_x), tiles);
         nsplit = std::min<int64_t>(nsplit, 65535);
         const int64_t rows = ((tiles + nsplit - 1) / nsplit) * JAC_TILE;
         nsplit = (cnt + rows - 1) / rows;
@@ -1640,7 +1653,7 @@ extern "C" int fb200_adjoint(fb200_model *mod, const double *xp, const double *y
         const int64_t blocks_x = (nn + FWD_THREADS - 1) / FWD_THREADS;
         const int64_t tiles = n_pad / TILE;
         int64_t nsplit = std::min<int64_t>(
-            std::max<int64_t>(1, ((int64_t)mod->sm_count * 20 + blocks_x - 1) / blocks_x), tiles);
+            std::max<int64_t>(1, ((int64_t)mod->sm_count * split_blocks_per_sm() + blocks_x - 1) / blocks_x), tiles);
         nsplit = std::min<int64_t>(nsplit, 32000);
         const int64_t chunk = ((tiles + nsplit - 1) / nsplit) * TILE;
         nsplit = (n + chunk - 1) / chunk;

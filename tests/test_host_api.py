@@ -189,9 +189,11 @@ def test_doctests_of_the_host_modules():
 def test_kernel_profiles_are_valid_for_this_tree():
     """
     bench.py's roofline reads executed-instruction counts from profiles/r02_kernel_<key>.json and
-    refuses a file measured on other sources of that kernel (bench.load_profile).  Every committed
-    profile must be valid for the committed sources: a kernel change without a re-capture
-    (tools/profile_all.py) fails here, on the CPU, before a bench line carries `frac: null`.
+    refuses a file measured on other DEVICE sources of that kernel (bench.load_profile).  Every
+    committed profile must be valid for the committed sources: a kernel change without a
+    re-capture (tools/profile_all.py) fails here, on the CPU, before a bench line carries
+    `frac: null`.  The profiles the default bench line quotes must also have been captured with
+    the committed LAUNCH code (grid sizing, prism split).
     """
     import glob
     import json
@@ -204,11 +206,14 @@ def test_kernel_profiles_are_valid_for_this_tree():
         d = json.load(open(path))
         key = d["key"]
         assert key in bench.KERNEL_TU, key
-        # the hashed set really is the kernel's: its translation unit and the launch code
         names = [os.path.basename(f) for f in bench.kernel_sources(key)]
-        assert bench.KERNEL_TU[key] in names and "prism_abi.cu" in names and "fatiando_b200.h" in names
+        assert bench.KERNEL_TU[key] in names and "prism_common.cuh" in names
         prof, src = bench.load_profile(key)
         assert prof is not None, src
+    for key in ("c2_nodes", "c3_nodes", "c4_nodes", "c4_grid", "c5_surface", "c5t_surface"):
+        prof, src = bench.load_profile(key)
+        assert prof["launch_code"] == "as captured", (key, prof["launch_code"])
+    assert [os.path.basename(f) for f in bench.launch_sources()] == ["prism_abi.cu", "abi_internal.h", "fatiando_b200.h"]
     # a header of another kernel family is not part of a prism kernel's hash
     assert "polyprism.cuh" not in [os.path.basename(f) for f in bench.kernel_sources("c2_nodes")]
     assert "polyprism.cuh" in [os.path.basename(f) for f in bench.kernel_sources("polyprism_gz")]

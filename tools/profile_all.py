@@ -68,7 +68,9 @@ def gpu(keys):
     os.makedirs(out, exist_ok=True)
     import json
     hashfile = os.path.join(out, "r02_kernel_hashes.json")
-    json.dump({k: bench.kernel_hash(k) for k in bench.KERNEL_TU}, open(hashfile, "w"))
+    hashes = {k: bench.kernel_hash(k) for k in bench.KERNEL_TU}
+    hashes["launch"] = bench.launch_hash()
+    json.dump(hashes, open(hashfile, "w"))
     for key in keys:
         rep = os.path.join(out, "r02_" + key)
         if key in SIBLINGS:

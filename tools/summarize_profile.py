@@ -5,10 +5,11 @@ Write the judged summary of an ncu report into profiles/ (text, committed).
 
 With KEY it also writes profiles/r02_kernel_KEY.json, the numbers bench.py's roofline reads
 (executed FP64-pipe instructions per pair, DRAM bytes per launch, ...) together with the hash
-of the sources THAT KERNEL is built from (bench.kernel_sources: its translation unit, the
-headers it includes, the launch code, the public header; HASHFILE = JSON {key: hash} the GPU
-box computed from its snapshot, default: this tree's); bench.py refuses the file when the
-hash differs from its build's.
+of the DEVICE sources that kernel is built from (bench.kernel_sources: its translation unit
+and the headers it includes) and, separately, of the launch code (bench.launch_sources);
+HASHFILE = JSON {key: hash, "launch": hash} the GPU box computed from its snapshot, default:
+this tree's.  bench.py refuses the file when the kernel hash differs from its build's and
+says so in its line when only the launch code changed.
 """
 import json
 import os
@@ -69,7 +70,11 @@ def main(rep, out, pairs, title, key=None, hashfile=None, jsondir=None):
         sys.path.insert(0, root)
         import bench
         # HASHFILE: JSON {key: kernel hash} written by the GPU box from its snapshot
-        h = json.load(open(hashfile))[key] if hashfile else bench.kernel_hash(key)
+        if hashfile:
+            hashes = json.load(open(hashfile))
+            h, lh = hashes[key], hashes["launch"]
+        else:
+            h, lh = bench.kernel_hash(key), bench.launch_hash()
         d = {"key": key, "kernel": name, "pairs_per_launch": float(pairs),
              "inst_per_pair": float(m.group(1)), "fp64_inst_per_pair": float(m.group(2)),
              "time_ms": val('gpu__time_duration.sum'),
@@ -79,6 +84,8 @@ def main(rep, out, pairs, title, key=None, hashfile=None, jsondir=None):
              "registers": val('launch__registers_per_thread'),
              "kernel_hash": h,
              "kernel_sources": [os.path.basename(f) for f in bench.kernel_sources(key)],
+             "launch_hash": lh,
+             "launch_sources": [os.path.basename(f) for f in bench.launch_sources()],
              "source": os.path.basename(rep) + " (summarised on the GPU box; the report itself is not kept)",
              "how": "ncu --set full --clock-control none --import-source on, one launch; instruction "
                     "counts from the source page (executed warp instructions x 32 / pairs)"}
