@@ -39,8 +39,11 @@ def _flatten(spheres, prop, override):
         if not override and prop == 'density':
             dens = numpy.ascontiguousarray(spheres.props['density'], dtype=numpy.float64)
         if not override and prop == 'magnetization':
-            mag = numpy.ascontiguousarray(spheres.props['magnetization'], dtype=numpy.float64).reshape(-1, 3)
-        return geo, dens, mag
+            mag = numpy.ascontiguousarray(spheres.props['magnetization'], dtype=numpy.float64)
+        # anything but one value (one vector) per point: per-point objects, as before
+        if (dens is None or dens.shape == (n,)) and (mag is None or mag.shape == (n, 3)) \
+                and all(a.shape == (n,) for a in geo):
+            return geo, dens, mag
     keep = [s for s in spheres
             if s is not None and (override or prop is None or prop in s.props)]
     geo = numpy.array([[s.x, s.y, s.z, s.radius] for s in keep], dtype=numpy.float64).reshape(-1, 4)
